@@ -1,0 +1,286 @@
+"""ctypes binding of include/dtr_b200.h plus a thin host-side mirror of the renderer's draw calls.
+
+``Renderer`` exposes the reference's draw-call set (DTRendererRender.h:91-98) with the same
+argument meaning -- clear / triangle / textured_triangle / mesh / rectangle / bitmap / line -- on
+top of the C ABI, so a scene written against the reference's API replays unchanged.  There is no
+CPU fallback: if libdtr_b200.so is missing or no CUDA device is present, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdtr_b200.so")
+
+SHADE_FULLBRIGHT, SHADE_FLAT, SHADE_GOURAUD = 0, 1, 2
+
+_f = C.POINTER(C.c_float)
+_u8 = C.POINTER(C.c_uint8)
+_i32 = C.POINTER(C.c_int32)
+_u32 = C.POINTER(C.c_uint32)
+
+
+class Transform(C.Structure):
+    """dtr_b200_transform == DTRRenderTransform (DTRendererRender.h:28-33)."""
+    _fields_ = [("rotation", C.c_float), ("anchor", C.c_float * 3), ("scale", C.c_float * 3)]
+
+
+class Light(C.Structure):
+    """dtr_b200_light == DTRRenderLight (DTRendererRender.h:72-77)."""
+    _fields_ = [("mode", C.c_int32), ("vector", C.c_float * 3), ("color", C.c_float * 4)]
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("vertexes", _f), ("numVertexes", C.c_uint32), ("texUV", _f), ("numTexUV", C.c_uint32),
+                ("normals", _f), ("numNormals", C.c_uint32), ("faces", _i32), ("numFaces", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("setPixels", C.c_uint64), ("triangles", C.c_uint64), ("primitives", C.c_uint64),
+                ("listEntries", C.c_uint64), ("kernelLaunches", C.c_uint64)]
+
+
+# every symbol include/dtr_b200.h declares: (name, restype, argtypes)
+_T = C.POINTER(Transform)
+_L = C.POINTER(Light)
+SYMBOLS = [
+    ("dtr_b200_create", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    ("dtr_b200_destroy", None, [C.c_void_p]),
+    ("dtr_b200_last_error", C.c_char_p, [C.c_void_p]),
+    ("dtr_b200_version", C.c_char_p, []),
+    ("dtr_b200_set_stream", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("dtr_b200_set_band", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("dtr_b200_upload_texture", C.c_int, [C.c_void_p, _u8, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    ("dtr_b200_upload_mesh", C.c_int, [C.c_void_p, C.POINTER(MeshDesc), C.c_int, C.POINTER(C.c_int)]),
+    ("dtr_b200_set_target", C.c_int, [C.c_void_p, C.c_int]),
+    ("dtr_b200_begin_frame", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    ("dtr_b200_flush", C.c_int, [C.c_void_p]),
+    ("dtr_b200_replay", C.c_int, [C.c_void_p]),
+    ("dtr_b200_sync", C.c_int, [C.c_void_p]),
+    ("dtr_b200_end_frame", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    ("dtr_b200_frame_device_ptrs", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    ("dtr_b200_get_stats", C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    ("dtr_b200_reset_stats", C.c_int, [C.c_void_p]),
+    ("dtr_b200_clear", C.c_int, [C.c_void_p, _f]),
+    ("dtr_b200_triangle", C.c_int, [C.c_void_p, _f, _f, _f, _f, _T]),
+    ("dtr_b200_triangles", C.c_int, [C.c_void_p, C.c_int, _f, _f, _T]),
+    ("dtr_b200_textured_triangle", C.c_int, [C.c_void_p, _f, _f, _f, _f, _f, _f, C.c_int, _f, _T]),
+    ("dtr_b200_mesh", C.c_int, [C.c_void_p, C.c_int, _L, _f, _T]),
+    ("dtr_b200_mesh_views", C.c_int, [C.c_void_p, C.c_int, _L, C.c_int, _f, _T, C.c_int]),
+    ("dtr_b200_rectangle", C.c_int, [C.c_void_p, _f, _f, _f, _T]),
+    ("dtr_b200_bitmap", C.c_int, [C.c_void_p, C.c_int, _f, _T, _f]),
+    ("dtr_b200_line", C.c_int, [C.c_void_p, _i32, _i32, _f]),
+]
+
+_lib = None
+
+
+def load_library():
+    """dlopen libdtr_b200.so and bind every symbol; raises if the CUDA module was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(this back end has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _fa(x, n=None):
+    a = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+    if n is not None and a.size != n:
+        raise ValueError(f"expected {n} floats, got {a.size}")
+    return a
+
+
+def _fp(a):
+    return a.ctypes.data_as(_f)
+
+
+def make_transform(t):
+    """Accept a Transform, a 7-float array (rotation, anchor.xyz, scale.xyz) or None."""
+    if t is None or isinstance(t, Transform):
+        return t
+    a = _fa(t, 7)
+    return Transform(float(a[0]), (C.c_float * 3)(*a[1:4]), (C.c_float * 3)(*a[4:7]))
+
+
+class DtrError(RuntimeError):
+    pass
+
+
+class Renderer:
+    """One rendering context on one GPU: ``num_frames`` colour+depth targets in HBM."""
+
+    def __init__(self, width, height, num_frames=1, device=0):
+        self.lib = load_library()
+        self.width, self.height, self.num_frames = width, height, num_frames
+        h = C.c_void_p()
+        rc = self.lib.dtr_b200_create(device, width, height, num_frames, C.byref(h))
+        if rc != 0:
+            raise DtrError(f"dtr_b200_create failed ({rc}): {self.lib.dtr_b200_last_error(None).decode()}")
+        self.ctx = h
+        self._tex = {}    # id(array) -> (texId, array)
+        self._mesh = {}   # (id(mesh dict), texId) -> meshId
+
+    # ---- plumbing ----------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise DtrError(f"dtr_b200 error {rc}: {self.lib.dtr_b200_last_error(self.ctx).decode()}")
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.dtr_b200_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        self._ck(self.lib.dtr_b200_set_stream(self.ctx, C.c_void_p(cuda_stream)))
+
+    def set_band(self, y0, y1):
+        self._ck(self.lib.dtr_b200_set_band(self.ctx, y0, y1))
+
+    def upload_texture(self, tex):
+        key = id(tex)
+        if key in self._tex:
+            return self._tex[key][0]
+        a = np.ascontiguousarray(tex, dtype=np.uint8)
+        h, w = a.shape[:2]
+        tid = C.c_int(-1)
+        self._ck(self.lib.dtr_b200_upload_texture(self.ctx, a.ctypes.data_as(_u8), w, h, 4, C.byref(tid)))
+        self._tex[key] = (tid.value, tex)
+        return tid.value
+
+    def upload_mesh(self, mesh, tex_id):
+        key = (id(mesh), tex_id)
+        if key in self._mesh:
+            return self._mesh[key][0]
+        v, t, n = _fa(mesh["vertexes"]), _fa(mesh["texUV"]), _fa(mesh["normals"])
+        f = np.ascontiguousarray(mesh["faces"], dtype=np.int32).reshape(-1)
+        d = MeshDesc(_fp(v), v.size // 4, _fp(t), t.size // 3, _fp(n), n.size // 3,
+                     f.ctypes.data_as(_i32), f.size // 9)
+        mid = C.c_int(-1)
+        self._ck(self.lib.dtr_b200_upload_mesh(self.ctx, C.byref(d), tex_id, C.byref(mid)))
+        self._mesh[key] = (mid.value, mesh)
+        return mid.value
+
+    # ---- frame -------------------------------------------------------------------------------
+    def set_target(self, frame):
+        self._ck(self.lib.dtr_b200_set_target(self.ctx, frame))
+
+    def begin_frame(self, frame=0, color=None, z=None):
+        cp = color.ctypes.data_as(C.c_void_p) if color is not None else None
+        zp = z.ctypes.data_as(C.c_void_p) if z is not None else None
+        self._ck(self.lib.dtr_b200_begin_frame(self.ctx, frame, cp, zp))
+
+    def flush(self):
+        self._ck(self.lib.dtr_b200_flush(self.ctx))
+
+    def replay(self):
+        self._ck(self.lib.dtr_b200_replay(self.ctx))
+
+    def sync(self):
+        self._ck(self.lib.dtr_b200_sync(self.ctx))
+
+    def end_frame(self, frame=0, want_z=True, color_out=None, z_out=None):
+        """Flush and read the frame back: returns (colour u32[H,W], depth f32[H,W] or None)."""
+        col = color_out if color_out is not None else np.empty((self.height, self.width), np.uint32)
+        z = z_out if z_out is not None else (np.empty((self.height, self.width), np.float32) if want_z else None)
+        self._ck(self.lib.dtr_b200_end_frame(self.ctx, frame, col.ctypes.data_as(C.c_void_p),
+                                             z.ctypes.data_as(C.c_void_p) if z is not None else None))
+        return col, z
+
+    def end_frame_ptr(self, frame, color_ptr, z_ptr=None):
+        """end_frame into caller-owned (e.g. pinned) host memory given as raw addresses."""
+        self._ck(self.lib.dtr_b200_end_frame(self.ctx, frame, C.c_void_p(color_ptr),
+                                             C.c_void_p(z_ptr) if z_ptr else None))
+
+    def frame_device_ptrs(self, frame=0):
+        c, z = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.dtr_b200_frame_device_ptrs(self.ctx, frame, C.byref(c), C.byref(z)))
+        return c.value, z.value
+
+    def stats(self):
+        s = Stats()
+        self._ck(self.lib.dtr_b200_get_stats(self.ctx, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
+
+    def reset_stats(self):
+        self._ck(self.lib.dtr_b200_reset_stats(self.ctx))
+
+    def counters(self):
+        s = self.stats()
+        return (s["setPixels"], s["triangles"])
+
+    # ---- draw calls (names and argument meaning of DTRendererRender.h:91-98) ------------------
+    def clear(self, rgb):
+        self._ck(self.lib.dtr_b200_clear(self.ctx, _fp(_fa(rgb, 3))))
+
+    def triangle(self, p, color, transform=None):
+        p = _fa(p, 9)
+        t = make_transform(transform)
+        self._ck(self.lib.dtr_b200_triangle(self.ctx, _fp(p[0:3]), _fp(p[3:6]), _fp(p[6:9]), _fp(_fa(color, 4)),
+                                            C.byref(t) if t else None))
+
+    def triangles(self, p, color, transform=None):
+        p = _fa(p)
+        n = p.size // 9
+        t = make_transform(transform)
+        self._ck(self.lib.dtr_b200_triangles(self.ctx, n, _fp(p), _fp(_fa(color, 4 * n)),
+                                             C.byref(t) if t else None))
+
+    def textured_triangle(self, p, uv, tex, color, transform=None):
+        p, uv = _fa(p, 9), _fa(uv, 6)
+        tid = self.upload_texture(tex) if tex is not None else -1
+        t = make_transform(transform)
+        self._ck(self.lib.dtr_b200_textured_triangle(self.ctx, _fp(p[0:3]), _fp(p[3:6]), _fp(p[6:9]),
+                                                     _fp(uv[0:2]), _fp(uv[2:4]), _fp(uv[4:6]), tid,
+                                                     _fp(_fa(color, 4)), C.byref(t) if t else None))
+
+    @staticmethod
+    def _light(light_mode, light_vector, light_color):
+        return Light(int(light_mode), (C.c_float * 3)(*_fa(light_vector, 3)), (C.c_float * 4)(*_fa(light_color, 4)))
+
+    def mesh(self, mesh, tex, light_mode, light_vector, light_color, pos=(0, 0, 0), transform=None):
+        tid = self.upload_texture(tex)
+        mid = self.upload_mesh(mesh, tid)
+        light = self._light(light_mode, light_vector, light_color)
+        t = make_transform(transform)
+        self._ck(self.lib.dtr_b200_mesh(self.ctx, mid, C.byref(light), _fp(_fa(pos, 3)), C.byref(t) if t else None))
+
+    def mesh_views(self, mesh, tex, light_mode, light_vector, light_color, positions, transforms, first_frame=0):
+        tid = self.upload_texture(tex)
+        mid = self.upload_mesh(mesh, tid)
+        light = self._light(light_mode, light_vector, light_color)
+        n = len(transforms)
+        arr = (Transform * n)(*[make_transform(t) for t in transforms])
+        self._ck(self.lib.dtr_b200_mesh_views(self.ctx, mid, C.byref(light), n, _fp(_fa(positions, 3 * n)), arr,
+                                              first_frame))
+
+    def rectangle(self, mn, mx, color, transform=None):
+        t = make_transform(transform)
+        self._ck(self.lib.dtr_b200_rectangle(self.ctx, _fp(_fa(mn, 2)), _fp(_fa(mx, 2)), _fp(_fa(color, 4)),
+                                             C.byref(t) if t else None))
+
+    def bitmap(self, tex, pos, transform=None, color=(1, 1, 1, 1)):
+        tid = self.upload_texture(tex)
+        t = make_transform(transform)
+        self._ck(self.lib.dtr_b200_bitmap(self.ctx, tid, _fp(_fa(pos, 2)), C.byref(t) if t else None,
+                                          _fp(_fa(color, 4))))
+
+    def line(self, a, b, color):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        b = np.ascontiguousarray(b, dtype=np.int32)
+        self._ck(self.lib.dtr_b200_line(self.ctx, a.ctypes.data_as(_i32), b.ctypes.data_as(_i32), _fp(_fa(color, 4))))

@@ -1,0 +1,803 @@
+// dtr_capi.cpp -- implementation of the C ABI in include/dtr_b200.h.
+//
+// Host side of the back end: records draw calls, evaluates the once-per-call host arithmetic
+// (dtr_host_math.h), uploads one command block per flush and launches
+//     setup_kernel -> scan_kernel -> bin_kernel -> raster_kernel
+// on the context's stream.  There is no CPU rendering path in this file: if CUDA is not
+// available dtr_b200_create fails.  Compiled with -ffp-contract=off.
+#include <cuda_runtime_api.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/dtr_b200.h"
+#include "dtr_host_math.h"
+#include "dtr_kernels.h"
+#include "dtr_records.h"
+
+using namespace dtr;
+
+namespace
+{
+
+std::string g_createError;
+
+struct DevBuf
+{
+	void  *p   = nullptr;
+	size_t cap = 0;
+};
+
+struct MeshAsset
+{
+	float   *vertexes = nullptr, *texUV = nullptr, *normals = nullptr;
+	int32_t *faces    = nullptr;
+	uint32_t numFaces = 0;
+	int      texId    = -1;
+};
+
+struct RecItem
+{
+	DrawItem item;
+	uint32_t frame;      // real frame index
+	uint32_t order;      // submission order (stable sort key)
+	size_t   payload[3]; // byte offsets into the payload buffer (valid where relocate[j])
+	bool     relocate[3];
+};
+
+struct FrameHost
+{
+	uint32_t pendingInit = 0; // FrameInit bits to apply at the next flush
+	uint32_t clearPacked = 0;
+	uint32_t recorded    = 0; // items recorded for this frame since the last flush
+};
+
+} // namespace
+
+struct dtr_b200_ctx
+{
+	int          device = 0, width = 0, height = 0, numFrames = 0;
+	cudaStream_t stream = nullptr, ownStream = nullptr;
+	uint32_t    *dColor = nullptr;
+	float       *dDepth = nullptr;
+	Geometry     geom{};
+	int          target = 0;
+
+	std::vector<FrameHost> frames;
+	std::vector<RecItem>   rec;
+	uint8_t               *payload = nullptr; // pinned
+	size_t                 payloadCap = 0, payloadUsed = 0;
+	uint8_t               *staging = nullptr; // pinned: FrameState[] + DrawItem[]
+	size_t                 stagingCap = 0;
+
+	std::vector<MeshAsset> meshes;
+	std::vector<TexDesc>   textures;
+	DevBuf                 dTextures;
+
+	DevBuf dCmd, dPayload, dPrims, dBounds, dTileCount, dTileOffset, dLists;
+	unsigned long long *dSetPixels = nullptr; // [0] = SetPixel count, [1] = list total of last scan
+	uint64_t            triangles = 0, launches = 0;
+
+	// last flush, for replay
+	struct
+	{
+		bool     valid = false;
+		uint32_t numActive = 0, numItems = 0, numPrims = 0;
+		uint64_t listTotal = 0, triangles = 0;
+		Geometry g{};
+	} last;
+
+	std::string err;
+};
+
+namespace
+{
+
+int fail(dtr_b200_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+	char buf[512];
+	if (e != cudaSuccess) snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+	else snprintf(buf, sizeof(buf), "%s", what);
+	if (c) c->err = buf;
+	else g_createError = buf;
+	return code;
+}
+
+#define CU(call)                                                              \
+	do                                                                        \
+	{                                                                         \
+		cudaError_t e_ = (call);                                              \
+		if (e_ != cudaSuccess) return fail(c, DTR_B200_ERR_CUDA, #call, e_);  \
+	} while (0)
+
+int ensure_dev(dtr_b200_ctx *c, DevBuf &b, size_t bytes)
+{
+	if (bytes <= b.cap) return 0;
+	size_t want = std::max(bytes, b.cap + b.cap / 2);
+	want        = (want + 255) & ~(size_t)255;
+	// buffers may still be in use by enqueued work
+	CU(cudaStreamSynchronize(c->stream));
+	if (b.p) CU(cudaFree(b.p));
+	b.p   = nullptr;
+	b.cap = 0;
+	CU(cudaMalloc(&b.p, want));
+	b.cap = want;
+	return 0;
+}
+
+int ensure_pinned(dtr_b200_ctx *c, uint8_t *&p, size_t &cap, size_t used, size_t bytes)
+{
+	if (bytes <= cap) return 0;
+	size_t   want = std::max(bytes, cap * 2);
+	want          = std::max<size_t>(want, 1 << 16);
+	uint8_t *n    = nullptr;
+	CU(cudaHostAlloc((void **)&n, want, cudaHostAllocDefault));
+	if (p)
+	{
+		if (used) memcpy(n, p, used);
+		cudaFreeHost(p);
+	}
+	p   = n;
+	cap = want;
+	return 0;
+}
+
+// append `bytes` to the pinned payload, 16-byte aligned; returns the byte offset
+int payload_push(dtr_b200_ctx *c, const void *src, size_t bytes, size_t *off)
+{
+	size_t at = (c->payloadUsed + 15) & ~(size_t)15;
+	int    rc = ensure_pinned(c, c->payload, c->payloadCap, c->payloadUsed, at + bytes);
+	if (rc) return rc;
+	memcpy(c->payload + at, src, bytes);
+	c->payloadUsed = at + bytes;
+	*off           = at;
+	return 0;
+}
+
+void set_geometry(dtr_b200_ctx *c, int y0, int y1)
+{
+	Geometry &g  = c->geom;
+	g.width      = c->width;
+	g.height     = c->height;
+	g.tilesX     = (c->width + TILE_W - 1) / TILE_W;
+	g.tilesY     = (c->height + TILE_H - 1) / TILE_H;
+	g.bandTileY0 = y0 / TILE_H;
+	g.bandTileY1 = (y1 + TILE_H - 1) / TILE_H;
+	g.bandTiles  = g.tilesX * (g.bandTileY1 - g.bandTileY0);
+	g.numFrames  = 0;
+}
+
+const dtr_b200_transform kDefaultTransform         = {0.0f, {0.5f, 0.5f, 0.5f}, {1.0f, 1.0f, 1.0f}};
+const dtr_b200_transform kDefaultTriangleTransform = {0.0f, {0.33f, 0.33f, 0.33f}, {1.0f, 1.0f, 1.0f}};
+
+RecItem &new_item(dtr_b200_ctx *c, uint32_t type, uint32_t frame, uint32_t count)
+{
+	c->rec.emplace_back();
+	RecItem &r = c->rec.back();
+	memset(&r, 0, sizeof(r));
+	r.item.type  = type;
+	r.item.count = count;
+	r.item.texId = -1;
+	r.frame      = frame;
+	r.order      = (uint32_t)c->rec.size() - 1;
+	c->frames[frame].recorded++;
+	return r;
+}
+
+int record_raw(dtr_b200_ctx *c, const PrimRecord &rec)
+{
+	size_t off;
+	int    rc = payload_push(c, &rec, sizeof(rec), &off);
+	if (rc) return rc;
+	RecItem &r    = new_item(c, ITEM_RAW, (uint32_t)c->target, 1);
+	r.payload[0]  = off;
+	r.relocate[0] = true;
+	return 0;
+}
+
+int record_tris(dtr_b200_ctx *c, int n, const float *p, const float *color, const float *uv, int texId,
+                const dtr_b200_transform *t)
+{
+	if (!t) t = &kDefaultTriangleTransform;
+	size_t offP, offC, offUV = 0;
+	int    rc;
+	if ((rc = payload_push(c, p, sizeof(float) * 9 * (size_t)n, &offP))) return rc;
+	if ((rc = payload_push(c, color, sizeof(float) * 4 * (size_t)n, &offC))) return rc;
+	if (uv && (rc = payload_push(c, uv, sizeof(float) * 6 * (size_t)n, &offUV))) return rc;
+	RecItem &r       = new_item(c, ITEM_TRIS, (uint32_t)c->target, (uint32_t)n);
+	r.payload[0]     = offP;
+	r.relocate[0]    = true;
+	r.payload[1]     = offC;
+	r.relocate[1]    = true;
+	r.payload[2]     = offUV;
+	r.relocate[2]    = (uv != nullptr);
+	r.item.texId     = texId;
+	r.item.lightMode = DTR_B200_SHADE_FULLBRIGHT; // NullRenderLightInternal (:1352-1356)
+	Basis2 b         = make_basis(t->rotation, t->scale[0], t->scale[1]);
+	r.item.xAxis[0] = b.xAxis[0]; r.item.xAxis[1] = b.xAxis[1];
+	r.item.yAxis[0] = b.yAxis[0]; r.item.yAxis[1] = b.yAxis[1];
+	r.item.anchor[0] = t->anchor[0];
+	r.item.anchor[1] = t->anchor[1];
+	c->triangles += (uint64_t)n;
+	return 0;
+}
+
+int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_t numPrims, bool replay)
+{
+	Geometry g   = c->geom;
+	g.numFrames  = (int32_t)numActive;
+	uint32_t numTiles = numActive * (uint32_t)g.bandTiles;
+	const FrameState *dFrames = (const FrameState *)c->dCmd.p;
+	const DrawItem   *dItems  = (const DrawItem *)((const uint8_t *)c->dCmd.p + sizeof(FrameState) * numActive);
+
+	int rc;
+	if ((rc = ensure_dev(c, c->dTileCount, sizeof(uint32_t) * (size_t)numTiles))) return rc;
+	if ((rc = ensure_dev(c, c->dTileOffset, sizeof(uint32_t) * (size_t)numTiles))) return rc;
+	if ((rc = ensure_dev(c, c->dPrims, sizeof(PrimRecord) * (size_t)std::max(numPrims, 1u)))) return rc;
+	if ((rc = ensure_dev(c, c->dBounds, sizeof(PrimBounds) * (size_t)std::max(numPrims, 1u)))) return rc;
+
+	CU(cudaMemsetAsync(c->dTileCount.p, 0, sizeof(uint32_t) * (size_t)numTiles, c->stream));
+	if (numPrims)
+	{
+		SetupParams S;
+		S.items     = dItems;
+		S.numItems  = (int)numItems;
+		S.numPrims  = numPrims;
+		S.prims     = (PrimRecord *)c->dPrims.p;
+		S.bounds    = (PrimBounds *)c->dBounds.p;
+		S.tileCount = (uint32_t *)c->dTileCount.p;
+		S.g         = g;
+		launch_setup(S, c->stream);
+		c->launches++;
+	}
+	launch_scan((const uint32_t *)c->dTileCount.p, (uint32_t *)c->dTileOffset.p, numTiles, c->dSetPixels + 1,
+	            c->stream);
+	c->launches++;
+
+	uint64_t total = c->last.listTotal;
+	if (!replay)
+	{
+		unsigned long long t = 0;
+		CU(cudaMemcpyAsync(&t, c->dSetPixels + 1, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+		total = t;
+		if (total >= (1ull << 31)) return fail(c, DTR_B200_ERR_OVERFLOW, "more than 2^31 (primitive, tile) pairs in one flush");
+		if ((rc = ensure_dev(c, c->dLists, sizeof(uint32_t) * (size_t)std::max<uint64_t>(total, 1)))) return rc;
+	}
+
+	if (numPrims && total)
+	{
+		BinParams B;
+		B.bounds       = (const PrimBounds *)c->dBounds.p;
+		B.frames       = dFrames;
+		B.tileCount    = (const uint32_t *)c->dTileCount.p;
+		B.tileOffset   = (const uint32_t *)c->dTileOffset.p;
+		B.lists        = (uint32_t *)c->dLists.p;
+		B.listCapacity = (uint32_t)(c->dLists.cap / sizeof(uint32_t));
+		B.g            = g;
+		launch_bin(B, c->stream);
+		c->launches++;
+	}
+
+	RasterParams R;
+	R.color      = c->dColor;
+	R.depth      = c->dDepth;
+	R.frames     = dFrames;
+	R.prims      = (const PrimRecord *)c->dPrims.p;
+	R.bounds     = (const PrimBounds *)c->dBounds.p;
+	R.tileCount  = (const uint32_t *)c->dTileCount.p;
+	R.tileOffset = (const uint32_t *)c->dTileOffset.p;
+	R.lists      = (const uint32_t *)c->dLists.p;
+	R.textures   = (const TexDesc *)c->dTextures.p;
+	R.setPixels  = c->dSetPixels;
+	R.g          = g;
+	launch_raster(R, c->stream);
+	c->launches++;
+	CU(cudaGetLastError());
+
+	c->last.valid     = true;
+	c->last.numActive = numActive;
+	c->last.numItems  = numItems;
+	c->last.numPrims  = numPrims;
+	c->last.listTotal = total;
+	c->last.g         = g;
+	return 0;
+}
+
+int do_flush(dtr_b200_ctx *c)
+{
+	// active frames: anything with recorded items or a pending on-chip init
+	std::vector<int32_t> slotOf(c->numFrames, -1);
+	std::vector<uint32_t> active;
+	for (int f = 0; f < c->numFrames; f++)
+		if (c->frames[f].recorded || c->frames[f].pendingInit)
+		{
+			slotOf[f] = (int32_t)active.size();
+			active.push_back((uint32_t)f);
+		}
+	if (active.empty()) return 0;
+
+	// frames are independent, so grouping items by frame (stable) preserves every frame's order
+	std::stable_sort(c->rec.begin(), c->rec.end(),
+	                 [](const RecItem &a, const RecItem &b) { return a.frame < b.frame; });
+
+	uint32_t numActive = (uint32_t)active.size(), numItems = (uint32_t)c->rec.size();
+	size_t   cmdBytes  = sizeof(FrameState) * numActive + sizeof(DrawItem) * numItems;
+	int      rc;
+	if ((rc = ensure_pinned(c, c->staging, c->stagingCap, 0, cmdBytes))) return rc;
+	if ((rc = ensure_dev(c, c->dCmd, cmdBytes))) return rc;
+	if ((rc = ensure_dev(c, c->dPayload, std::max<size_t>(c->payloadUsed, 16)))) return rc;
+
+	FrameState *fs = (FrameState *)c->staging;
+	DrawItem   *it = (DrawItem *)(c->staging + sizeof(FrameState) * numActive);
+	for (uint32_t s = 0; s < numActive; s++)
+	{
+		FrameHost &fh     = c->frames[active[s]];
+		fs[s].init        = fh.pendingInit;
+		fs[s].clearPacked = fh.clearPacked;
+		fs[s].primBegin = fs[s].primEnd = 0;
+		fs[s].frameIndex = active[s];
+		fs[s].pad[0] = fs[s].pad[1] = fs[s].pad[2] = 0;
+	}
+	uint64_t prim = 0;
+	int32_t  cur  = -1;
+	for (uint32_t i = 0; i < numItems; i++)
+	{
+		RecItem &r    = c->rec[i];
+		int32_t  slot = slotOf[r.frame];
+		if (slot != cur)
+		{
+			if (cur >= 0) fs[cur].primEnd = (uint32_t)prim;
+			fs[slot].primBegin = (uint32_t)prim;
+			cur                = slot;
+		}
+		r.item.frame    = (uint32_t)slot;
+		r.item.primBase = (uint32_t)prim;
+		for (int j = 0; j < 3; j++)
+			if (r.relocate[j]) r.item.ptr[j] = (uint64_t)((uint8_t *)c->dPayload.p + r.payload[j]);
+		it[i] = r.item;
+		prim += r.item.count;
+		if (prim >= (1ull << 31)) return fail(c, DTR_B200_ERR_OVERFLOW, "more than 2^31 primitives in one flush");
+	}
+	if (cur >= 0) fs[cur].primEnd = (uint32_t)prim;
+	// slots with no items keep primBegin == primEnd
+	for (uint32_t s = 0; s < numActive; s++)
+		if (c->frames[active[s]].recorded == 0) fs[s].primBegin = fs[s].primEnd = 0;
+
+	CU(cudaMemcpyAsync(c->dCmd.p, c->staging, cmdBytes, cudaMemcpyHostToDevice, c->stream));
+	if (c->payloadUsed)
+		CU(cudaMemcpyAsync(c->dPayload.p, c->payload, c->payloadUsed, cudaMemcpyHostToDevice, c->stream));
+
+	rc = run_pipeline(c, numActive, numItems, (uint32_t)prim, false);
+	// the host copies were consumed (run_pipeline synchronises before binning)
+	for (uint32_t s = 0; s < numActive; s++)
+	{
+		FrameHost &fh  = c->frames[active[s]];
+		fh.pendingInit = 0;
+		fh.recorded    = 0;
+	}
+	c->rec.clear();
+	c->payloadUsed = 0;
+	return rc;
+}
+
+bool valid_frame(const dtr_b200_ctx *c, int f) { return f >= 0 && f < c->numFrames; }
+
+} // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char *dtr_b200_version(void) { return "dtr_b200 0.1 (sm_100a)"; }
+
+const char *dtr_b200_last_error(const dtr_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
+
+int dtr_b200_create(int device, int width, int height, int numFrames, dtr_b200_ctx **out)
+{
+	dtr_b200_ctx *c = nullptr; // for CU(): errors land in g_createError
+	if (!out) return fail(nullptr, DTR_B200_ERR_ARG, "out is NULL");
+	*out = nullptr;
+	if (width <= 0 || height <= 0 || width > 16384 || height > 16384 || numFrames <= 0)
+		return fail(nullptr, DTR_B200_ERR_ARG, "width/height must be in [1,16384] and numFrames >= 1");
+	int count = 0;
+	CU(cudaGetDeviceCount(&count));
+	if (device < 0 || device >= count) return fail(nullptr, DTR_B200_ERR_CUDA, "no such CUDA device (this back end has no CPU fallback)");
+	CU(cudaSetDevice(device));
+	dtr_b200_ctx *n = new (std::nothrow) dtr_b200_ctx();
+	if (!n) return fail(nullptr, DTR_B200_ERR_NOMEM, "out of host memory");
+	n->device    = device;
+	n->width     = width;
+	n->height    = height;
+	n->numFrames = numFrames;
+	n->frames.resize(numFrames);
+	size_t plane = (size_t)width * height;
+	cudaError_t e;
+	if ((e = cudaStreamCreateWithFlags(&n->ownStream, cudaStreamNonBlocking)) != cudaSuccess ||
+	    (e = cudaMalloc((void **)&n->dColor, plane * numFrames * sizeof(uint32_t))) != cudaSuccess ||
+	    (e = cudaMalloc((void **)&n->dDepth, plane * numFrames * sizeof(float))) != cudaSuccess ||
+	    (e = cudaMalloc((void **)&n->dSetPixels, 2 * sizeof(unsigned long long))) != cudaSuccess ||
+	    (e = cudaMemset(n->dColor, 0, plane * numFrames * sizeof(uint32_t))) != cudaSuccess ||
+	    (e = cudaMemset(n->dSetPixels, 0, 2 * sizeof(unsigned long long))) != cudaSuccess)
+	{
+		fail(nullptr, DTR_B200_ERR_CUDA, "allocating frame targets", e);
+		dtr_b200_destroy(n);
+		return DTR_B200_ERR_CUDA;
+	}
+	n->stream = n->ownStream;
+	set_geometry(n, 0, height);
+	// a frame that was never begun starts like the reference's first frame: depth reset
+	for (auto &f : n->frames) f.pendingInit = FI_Z_RESET;
+	*out = n;
+	return DTR_B200_OK;
+}
+
+void dtr_b200_destroy(dtr_b200_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	for (auto &m : c->meshes)
+	{
+		cudaFree(m.vertexes);
+		cudaFree(m.texUV);
+		cudaFree(m.normals);
+		cudaFree(m.faces);
+	}
+	for (auto &t : c->textures) cudaFree((void *)t.texels);
+	DevBuf *bufs[] = {&c->dTextures, &c->dCmd, &c->dPayload, &c->dPrims, &c->dBounds, &c->dTileCount, &c->dTileOffset, &c->dLists};
+	for (DevBuf *b : bufs) cudaFree(b->p);
+	cudaFree(c->dColor);
+	cudaFree(c->dDepth);
+	cudaFree(c->dSetPixels);
+	if (c->payload) cudaFreeHost(c->payload);
+	if (c->staging) cudaFreeHost(c->staging);
+	if (c->ownStream) cudaStreamDestroy(c->ownStream);
+	delete c;
+}
+
+int dtr_b200_set_stream(dtr_b200_ctx *c, void *cudaStream)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	CU(cudaSetDevice(c->device));
+	int rc = do_flush(c);
+	if (rc) return rc;
+	CU(cudaStreamSynchronize(c->stream));
+	c->stream = cudaStream ? (cudaStream_t)cudaStream : c->ownStream;
+	return DTR_B200_OK;
+}
+
+int dtr_b200_set_band(dtr_b200_ctx *c, int y0, int y1)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (y0 < 0 || y1 > c->height || y0 >= y1 || (y0 % TILE_H) != 0 || ((y1 % TILE_H) != 0 && y1 != c->height))
+		return fail(c, DTR_B200_ERR_ARG, "band must be tile aligned (multiples of 32 rows, or end at height)");
+	CU(cudaSetDevice(c->device));
+	int rc = do_flush(c);
+	if (rc) return rc;
+	set_geometry(c, y0, y1);
+	c->last.valid = false;
+	return DTR_B200_OK;
+}
+
+int dtr_b200_upload_texture(dtr_b200_ctx *c, const uint8_t *texels, int width, int height, int bytesPerPixel, int *texId)
+{
+	if (!c || !texId) return DTR_B200_ERR_ARG;
+	if (!texels || width <= 0 || height <= 0 || width > 32767 || height > 32767 || bytesPerPixel != 4)
+		return fail(c, DTR_B200_ERR_ARG, "texture must be non-NULL RGBA8 with dimensions in [1,32767]");
+	CU(cudaSetDevice(c->device));
+	uint32_t *d     = nullptr;
+	size_t    bytes = (size_t)width * height * 4;
+	CU(cudaMalloc((void **)&d, bytes));
+	CU(cudaMemcpy(d, texels, bytes, cudaMemcpyHostToDevice));
+	c->textures.push_back(TexDesc{d, width, height});
+	CU(cudaStreamSynchronize(c->stream)); // the old table may be in use
+	int rc = ensure_dev(c, c->dTextures, sizeof(TexDesc) * std::max<size_t>(c->textures.capacity(), 16));
+	if (rc) return rc;
+	CU(cudaMemcpy(c->dTextures.p, c->textures.data(), sizeof(TexDesc) * c->textures.size(), cudaMemcpyHostToDevice));
+	*texId = (int)c->textures.size() - 1;
+	return DTR_B200_OK;
+}
+
+int dtr_b200_upload_mesh(dtr_b200_ctx *c, const dtr_b200_mesh_desc *m, int texId, int *meshId)
+{
+	if (!c || !meshId) return DTR_B200_ERR_ARG;
+	if (!m || !m->vertexes || !m->texUV || !m->normals || !m->faces || !m->numFaces)
+		return fail(c, DTR_B200_ERR_ARG, "mesh needs vertexes, texUV, normals and faces");
+	if (texId >= (int)c->textures.size()) return fail(c, DTR_B200_ERR_ARG, "texId out of range");
+	// the reference asserts on out-of-range indices (DTRendererRender.cpp:1450-1502)
+	for (size_t i = 0; i < (size_t)m->numFaces * 9; i++)
+	{
+		int32_t  idx = m->faces[i];
+		uint32_t lim = (i % 9 < 3) ? m->numVertexes : ((i % 9 < 6) ? m->numTexUV : m->numNormals);
+		if (idx < 0 || (uint32_t)idx >= lim) return fail(c, DTR_B200_ERR_ARG, "face index out of range");
+	}
+	CU(cudaSetDevice(c->device));
+	MeshAsset a;
+	a.numFaces = m->numFaces;
+	a.texId    = texId;
+	CU(cudaMalloc((void **)&a.vertexes, sizeof(float) * 4 * m->numVertexes));
+	CU(cudaMalloc((void **)&a.texUV, sizeof(float) * 3 * m->numTexUV));
+	CU(cudaMalloc((void **)&a.normals, sizeof(float) * 3 * m->numNormals));
+	CU(cudaMalloc((void **)&a.faces, sizeof(int32_t) * 9 * m->numFaces));
+	CU(cudaMemcpy(a.vertexes, m->vertexes, sizeof(float) * 4 * m->numVertexes, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(a.texUV, m->texUV, sizeof(float) * 3 * m->numTexUV, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(a.normals, m->normals, sizeof(float) * 3 * m->numNormals, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(a.faces, m->faces, sizeof(int32_t) * 9 * m->numFaces, cudaMemcpyHostToDevice));
+	c->meshes.push_back(a);
+	*meshId = (int)c->meshes.size() - 1;
+	return DTR_B200_OK;
+}
+
+int dtr_b200_set_target(dtr_b200_ctx *c, int frame)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (!valid_frame(c, frame)) return fail(c, DTR_B200_ERR_ARG, "frame out of range");
+	c->target = frame;
+	return DTR_B200_OK;
+}
+
+int dtr_b200_begin_frame(dtr_b200_ctx *c, int frame, const uint32_t *hostColor, const float *hostZ)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (!valid_frame(c, frame)) return fail(c, DTR_B200_ERR_ARG, "frame out of range");
+	CU(cudaSetDevice(c->device));
+	if (c->frames[frame].recorded)
+	{
+		int rc = do_flush(c);
+		if (rc) return rc;
+	}
+	size_t     plane = (size_t)c->width * c->height;
+	FrameHost &fh    = c->frames[frame];
+	fh.pendingInit   = 0;
+	if (hostZ) CU(cudaMemcpyAsync(c->dDepth + plane * frame, hostZ, plane * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+	else fh.pendingInit |= FI_Z_RESET;
+	if (hostColor)
+		CU(cudaMemcpyAsync(c->dColor + plane * frame, hostColor, plane * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+	c->target = frame;
+	return DTR_B200_OK;
+}
+
+int dtr_b200_flush(dtr_b200_ctx *c)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	CU(cudaSetDevice(c->device));
+	return do_flush(c);
+}
+
+int dtr_b200_replay(dtr_b200_ctx *c)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (!c->last.valid) return fail(c, DTR_B200_ERR_ARG, "nothing to replay");
+	if (!c->rec.empty()) return fail(c, DTR_B200_ERR_ARG, "replay with unflushed draw calls pending");
+	CU(cudaSetDevice(c->device));
+	return run_pipeline(c, c->last.numActive, c->last.numItems, c->last.numPrims, true);
+}
+
+int dtr_b200_sync(dtr_b200_ctx *c)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	return DTR_B200_OK;
+}
+
+int dtr_b200_end_frame(dtr_b200_ctx *c, int frame, uint32_t *hostColor, float *hostZ)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (!valid_frame(c, frame)) return fail(c, DTR_B200_ERR_ARG, "frame out of range");
+	CU(cudaSetDevice(c->device));
+	int rc = do_flush(c);
+	if (rc) return rc;
+	size_t plane = (size_t)c->width * c->height;
+	if (hostColor)
+		CU(cudaMemcpyAsync(hostColor, c->dColor + plane * frame, plane * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	if (hostZ) CU(cudaMemcpyAsync(hostZ, c->dDepth + plane * frame, plane * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return DTR_B200_OK;
+}
+
+int dtr_b200_frame_device_ptrs(dtr_b200_ctx *c, int frame, void **color, void **z)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (!valid_frame(c, frame)) return fail(c, DTR_B200_ERR_ARG, "frame out of range");
+	size_t plane = (size_t)c->width * c->height;
+	if (color) *color = c->dColor + plane * frame;
+	if (z) *z = c->dDepth + plane * frame;
+	return DTR_B200_OK;
+}
+
+int dtr_b200_get_stats(dtr_b200_ctx *c, dtr_b200_stats *out)
+{
+	if (!c || !out) return DTR_B200_ERR_ARG;
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	unsigned long long sp = 0;
+	CU(cudaMemcpy(&sp, c->dSetPixels, sizeof(sp), cudaMemcpyDeviceToHost));
+	out->setPixels      = sp;
+	out->triangles      = c->triangles;
+	out->primitives     = c->last.numPrims;
+	out->listEntries    = c->last.listTotal;
+	out->kernelLaunches = c->launches;
+	return DTR_B200_OK;
+}
+
+int dtr_b200_reset_stats(dtr_b200_ctx *c)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaMemset(c->dSetPixels, 0, sizeof(unsigned long long)));
+	c->triangles = 0;
+	c->launches  = 0;
+	return DTR_B200_OK;
+}
+
+// ---- draw calls ---------------------------------------------------------------------------------
+
+int dtr_b200_clear(dtr_b200_ctx *c, const float rgb[3])
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (!rgb) return DTR_B200_OK;
+	uint32_t   packed = pack_clear(rgb);
+	FrameHost &fh     = c->frames[c->target];
+	if (fh.recorded == 0)
+	{
+		// first command of the batch for this frame: the tile kernel generates the colour on chip
+		fh.pendingInit |= FI_COLOR_CLEAR;
+		fh.clearPacked = packed;
+		return DTR_B200_OK;
+	}
+	PrimRecord r;
+	memset(&r, 0, sizeof(r));
+	r.w[QW_FLAGS]  = PRIM_CLEAR;
+	r.w[QW_MIN]    = 0;
+	r.w[QW_MAX]    = (uint32_t)c->width | ((uint32_t)c->height << 16);
+	r.w[QW_PACKED] = packed;
+	return record_raw(c, r);
+}
+
+int dtr_b200_triangle(dtr_b200_ctx *c, const float p1[3], const float p2[3], const float p3[3],
+                      const float color[4], const dtr_b200_transform *t)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (!p1 || !p2 || !p3 || !color) return DTR_B200_OK;
+	float p[9] = {p1[0], p1[1], p1[2], p2[0], p2[1], p2[2], p3[0], p3[1], p3[2]};
+	return record_tris(c, 1, p, color, nullptr, -1, t);
+}
+
+int dtr_b200_triangles(dtr_b200_ctx *c, int n, const float *p, const float *color, const dtr_b200_transform *t)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (n <= 0 || !p || !color) return DTR_B200_OK;
+	return record_tris(c, n, p, color, nullptr, -1, t);
+}
+
+int dtr_b200_textured_triangle(dtr_b200_ctx *c, const float p1[3], const float p2[3], const float p3[3],
+                               const float uv1[2], const float uv2[2], const float uv3[2], int texId,
+                               const float color[4], const dtr_b200_transform *t)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (!p1 || !p2 || !p3 || !uv1 || !uv2 || !uv3 || !color) return DTR_B200_OK;
+	if (texId >= (int)c->textures.size()) return fail(c, DTR_B200_ERR_ARG, "texId out of range");
+	float p[9]  = {p1[0], p1[1], p1[2], p2[0], p2[1], p2[2], p3[0], p3[1], p3[2]};
+	float uv[6] = {uv1[0], uv1[1], uv2[0], uv2[1], uv3[0], uv3[1]};
+	return record_tris(c, 1, p, color, uv, texId < 0 ? -1 : texId, t);
+}
+
+int dtr_b200_mesh_views(dtr_b200_ctx *c, int meshId, const dtr_b200_light *light, int nViews, const float *pos,
+                        const dtr_b200_transform *transforms, int firstFrame)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (!light || !pos || !transforms || nViews <= 0) return DTR_B200_OK;
+	if (meshId < 0 || meshId >= (int)c->meshes.size()) return fail(c, DTR_B200_ERR_ARG, "meshId out of range");
+	if (!valid_frame(c, firstFrame) || !valid_frame(c, firstFrame + nViews - 1))
+		return fail(c, DTR_B200_ERR_ARG, "views do not fit the context's frames");
+	const MeshAsset &m = c->meshes[meshId];
+	Basis2           b = make_basis(0.0f, 1.0f, 1.0f); // DTRRender_DefaultTriangleTransform()
+	for (int v = 0; v < nViews; v++)
+	{
+		const dtr_b200_transform &t = transforms[v];
+		Mat4     M = mesh_matrix(c->width, c->height, pos + 3 * v, t.rotation, t.anchor, t.scale);
+		RecItem &r = new_item(c, ITEM_MESH, (uint32_t)(firstFrame + v), m.numFaces);
+		r.item.texId     = m.texId; // DTRRender_Mesh always samples mesh->tex (:1563-1564)
+		r.item.lightMode = (uint32_t)light->mode;
+		r.item.ptr[0]    = (uint64_t)m.vertexes;
+		r.item.ptr[1]    = (uint64_t)m.texUV;
+		r.item.ptr[2]    = (uint64_t)m.normals;
+		r.item.ptr[3]    = (uint64_t)m.faces;
+		r.item.xAxis[0] = b.xAxis[0]; r.item.xAxis[1] = b.xAxis[1];
+		r.item.yAxis[0] = b.yAxis[0]; r.item.yAxis[1] = b.yAxis[1];
+		r.item.anchor[0] = 0.33f;
+		r.item.anchor[1] = 0.33f;
+		memcpy(r.item.m, M.e, sizeof(float) * 16);
+		r.item.lightVec[0] = light->vector[0];
+		r.item.lightVec[1] = light->vector[1];
+		r.item.lightVec[2] = light->vector[2];
+		memcpy(r.item.color, light->color, sizeof(float) * 4);
+		c->triangles += m.numFaces;
+	}
+	return DTR_B200_OK;
+}
+
+int dtr_b200_mesh(dtr_b200_ctx *c, int meshId, const dtr_b200_light *light, const float pos[3],
+                  const dtr_b200_transform *t)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (!t) t = &kDefaultTransform;
+	return dtr_b200_mesh_views(c, meshId, light, 1, pos, t, c->target);
+}
+
+int dtr_b200_rectangle(dtr_b200_ctx *c, const float mn[2], const float mx[2], const float color[4],
+                       const dtr_b200_transform *t)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (!mn || !mx || !color) return DTR_B200_OK;
+	if (!t) t = &kDefaultTransform;
+	PrimRecord r;
+	if (!setup_quad(c->width, c->height, mn, mx, t->rotation, t->anchor, t->scale, color, false, -1, 0, 0, &r))
+		return DTR_B200_OK;
+	return record_raw(c, r);
+}
+
+int dtr_b200_bitmap(dtr_b200_ctx *c, int texId, const float pos[2], const dtr_b200_transform *t, const float color[4])
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (!pos) return DTR_B200_OK;
+	if (texId < 0 || texId >= (int)c->textures.size()) return fail(c, DTR_B200_ERR_ARG, "texId out of range");
+	if (!t) t = &kDefaultTransform;
+	const float white[4] = {1, 1, 1, 1};
+	if (!color) color = white;
+	const TexDesc &td    = c->textures[texId];
+	float          mn[2] = {pos[0], pos[1]};
+	float          mx[2] = {pos[0] + (float)td.w, pos[1] + (float)td.h}; // min + dim (:1607-1608)
+	PrimRecord     r;
+	if (!setup_quad(c->width, c->height, mn, mx, t->rotation, t->anchor, t->scale, color, true, texId, td.w, td.h, &r))
+		return DTR_B200_OK;
+	return record_raw(c, r);
+}
+
+int dtr_b200_line(dtr_b200_ctx *c, const int32_t a[2], const int32_t b[2], const float color[4])
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (!a || !b || !color) return DTR_B200_OK;
+	// DTRRender_Line (:294-356): x-major integer DDA after the optional axis swap
+	int ax = a[0], ay = a[1], bx = b[0], by = b[1];
+	int steep = std::abs(ax - bx) < std::abs(ay - by);
+	if (steep) { std::swap(ax, ay); std::swap(bx, by); }
+	if (bx < ax) { std::swap(ax, bx); std::swap(ay, by); }
+	int run = bx - ax, rise = by - ay;
+	if (run <= 0) return DTR_B200_OK;
+	int delta = (by > ay) ? 1 : -1;
+	// pixel bbox in screen orientation, clipped (SetPixel rejects the rest, :129-130)
+	int majLo = ax, majHi = ax + run; // [lo, hi)
+	int minLo = std::min(ay, by), minHi = std::max(ay, by) + 1;
+	int x0 = steep ? minLo : majLo, x1 = steep ? minHi : majHi, y0 = steep ? majLo : minLo, y1 = steep ? majHi : minHi;
+	x0 = clampi(x0, 0, c->width); x1 = clampi(x1, 0, c->width);
+	y0 = clampi(y0, 0, c->height); y1 = clampi(y1, 0, c->height);
+	if (x1 <= x0 || y1 <= y0) return DTR_B200_OK;
+	float col[4];
+	to_linear_premul(color, col);
+	PrimRecord r;
+	memset(&r, 0, sizeof(r));
+	r.w[QW_FLAGS] = PRIM_LINE;
+	r.w[QW_MIN]   = (uint32_t)x0 | ((uint32_t)y0 << 16);
+	r.w[QW_MAX]   = (uint32_t)x1 | ((uint32_t)y1 << 16);
+	for (int i = 0; i < 4; i++) r.w[QW_COLOR + i] = f2u(col[i]);
+	r.w[QW_LINE + 0] = (uint32_t)ax;
+	r.w[QW_LINE + 1] = (uint32_t)ay;
+	r.w[QW_LINE + 2] = (uint32_t)run;
+	r.w[QW_LINE + 3] = (uint32_t)(std::abs(rise) * 2);
+	r.w[QW_LINE + 4] = (uint32_t)delta;
+	r.w[QW_LINE + 5] = (uint32_t)steep;
+	return record_raw(c, r);
+}
+
+} // extern "C"

@@ -1,0 +1,52 @@
+// dtr_kernels.h -- parameter blocks and launchers of the sm_100a kernels (dtr_kernels.cu).
+#pragma once
+#include <cuda_runtime_api.h>
+
+#include "dtr_records.h"
+
+namespace dtr
+{
+
+struct SetupParams
+{
+	const DrawItem *items;
+	int             numItems;
+	uint32_t        numPrims;
+	PrimRecord     *prims;
+	PrimBounds     *bounds;
+	uint32_t       *tileCount; // [numFrames * bandTiles]
+	Geometry        g;
+};
+
+struct BinParams
+{
+	const PrimBounds *bounds;
+	const FrameState *frames;
+	const uint32_t   *tileCount;
+	const uint32_t   *tileOffset;
+	uint32_t         *lists;
+	uint32_t          listCapacity;
+	Geometry          g;
+};
+
+struct RasterParams
+{
+	uint32_t           *color; // [F][H][W]
+	float              *depth;
+	const FrameState   *frames;
+	const PrimRecord   *prims;
+	const PrimBounds   *bounds;
+	const uint32_t     *tileCount;
+	const uint32_t     *tileOffset;
+	const uint32_t     *lists;
+	const TexDesc      *textures;
+	unsigned long long *setPixels;
+	Geometry            g;
+};
+
+void launch_setup(const SetupParams &P, cudaStream_t s);
+void launch_scan(const uint32_t *counts, uint32_t *offsets, uint32_t n, unsigned long long *total, cudaStream_t s);
+void launch_bin(const BinParams &P, cudaStream_t s);
+void launch_raster(const RasterParams &P, cudaStream_t s);
+
+} // namespace dtr

@@ -1,0 +1,134 @@
+// dtr_records.h -- POD records shared by the host recorder and the sm_100a kernels.
+//
+// Data layout in HBM:
+//   frames        colour u32[F][H][W] (0x00RRGGBB) and depth f32[F][H][W], row 0 = bottom --
+//                 exactly DTRRenderBuffer's planes (DTRendererRender.h:14-25), one pair per frame.
+//   DrawItem[]    one per recorded draw call (tiny), uploaded per flush.
+//   PrimRecord[]  one 160-byte record per primitive in submission order, written by the setup
+//                 kernel, read by the raster kernel as ten 128-bit broadcast loads.
+//   PrimBounds[]  8 bytes per primitive (pixel bbox, half open) -- what binning scans.
+//   tile lists    u32 primitive indices per (frame, tile), ascending = submission order.
+#pragma once
+#include <stdint.h>
+
+namespace dtr
+{
+
+// Screen tile owned by one CTA of the raster kernel; each of its 8 warps owns a 16x16 region
+// that it walks in 8x4-pixel sub-blocks (one pixel per lane).
+constexpr int TILE_W      = 64;
+constexpr int TILE_H      = 32;
+constexpr int REGION_W    = 16;
+constexpr int REGION_H    = 16;
+constexpr int SUB_W       = 8;
+constexpr int SUB_H       = 4;
+constexpr int RASTER_THREADS = 256;
+
+enum PrimType : uint32_t
+{
+	PRIM_TRI       = 0, // edge-function triangle (DTRendererRender.cpp:1071-1236)
+	PRIM_RECT_FILL = 1, // axis-aligned rectangle fill (:472-483)
+	PRIM_RECT_ROT  = 2, // rotated rectangle, 4-edge inside test (:442-471)
+	PRIM_BITMAP    = 3, // bilinear bitmap blit (:1596-1791)
+	PRIM_CLEAR     = 4, // colour-only clear (:1793-1815)
+	PRIM_LINE      = 5, // integer DDA line (:294-356)
+};
+
+enum PrimFlags : uint32_t
+{
+	PF_TYPE_MASK    = 0xF,
+	PF_EXACT        = 1u << 4, // integer-valued edge setup: direct evaluation == sequential adds
+	PF_IGNORE_LIGHT = 1u << 5,
+	PF_TEXTURED     = 1u << 6,
+};
+
+// 40 words.  Word indices of the triangle layout:
+enum TriWord
+{
+	TW_FLAGS = 0, TW_TEX = 1, TW_MIN = 2 /* minx | miny<<16 */, TW_MAX = 3 /* maxx | maxy<<16 */,
+	TW_E0 = 4 /*3*/, TW_DX = 7 /*3*/, TW_DY = 10 /*3*/, TW_INV_AREA = 13, TW_Z1 = 14, TW_DZ2 = 15,
+	TW_DZ3 = 16, TW_COLOR = 17 /*4: linear premultiplied rgba*/, TW_LIGHT = 21 /*9: [vertex][rgb]*/,
+	TW_UV1 = 30 /*2*/, TW_DUV2 = 32 /*2*/, TW_DUV3 = 34 /*2*/,
+};
+// Word indices of the quad layout (rectangle / bitmap / clear / line):
+enum QuadWord
+{
+	QW_FLAGS = 0, QW_TEX = 1, QW_MIN = 2, QW_MAX = 3,
+	QW_P = 4 /*8: Basis, XAxis, Point, YAxis (x,y)*/, QW_COLOR = 12 /*4*/, QW_INVX = 16, QW_INVY = 17,
+	QW_TEXDIM = 18 /* w | h<<16 */, QW_PACKED = 19 /* PRIM_CLEAR: packed 0x00RRGGBB */,
+	QW_LINE = 20 /*6: ax, ay, run, dist, delta, steep */,
+};
+
+struct alignas(16) PrimRecord
+{
+	uint32_t w[40];
+};
+static_assert(sizeof(PrimRecord) == 160, "PrimRecord must be ten 128-bit words");
+
+struct PrimBounds
+{
+	uint32_t mn; // minx | miny << 16
+	uint32_t mx; // maxx | maxy << 16 (exclusive); mx <= mn component-wise means "never binned"
+};
+
+enum ItemType : uint32_t
+{
+	ITEM_TRIS = 0, // count triangles from host arrays p/color(/uv)
+	ITEM_MESH = 1, // count faces of an uploaded mesh through one host-built matrix
+	ITEM_RAW  = 2, // count == 1: a PrimRecord computed on the host (rectangle, bitmap, clear, line)
+};
+
+struct alignas(16) DrawItem
+{
+	uint32_t type;
+	uint32_t frame;
+	uint32_t primBase; // global index of this item's first primitive
+	uint32_t count;
+	int32_t  texId; // < 0: untextured
+	uint32_t lightMode;
+	uint32_t pad0, pad1;
+	// ITEM_TRIS: device pointers to p f32[count*9], color f32[count*4], uv f32[count*6] (or 0)
+	// ITEM_MESH: vertexes, texUV, normals, faces
+	// ITEM_RAW : record
+	uint64_t ptr[4];
+	float xAxis[2], yAxis[2]; // host cosf/sinf * scale (DTRendererRender.cpp:282-285)
+	float anchor[2];
+	float pad2[2];
+	float m[16];              // ITEM_MESH: viewport*persp*view*model, e[col][row]
+	float lightVec[3];
+	float pad3;
+	float color[4];
+};
+static_assert(sizeof(DrawItem) % 16 == 0, "DrawItem must stay 16-byte aligned");
+
+struct TexDesc
+{
+	const uint32_t *texels;
+	int32_t         w, h;
+};
+
+enum FrameInit : uint32_t
+{
+	FI_Z_RESET     = 1u << 0, // depth starts at -FLT_MAX, generated on chip (no read)
+	FI_COLOR_CLEAR = 1u << 1, // colour starts at clearPacked, generated on chip (no read)
+};
+
+struct FrameState
+{
+	uint32_t init;
+	uint32_t clearPacked;
+	uint32_t primBegin, primEnd; // this frame's contiguous primitive range in the flush
+	uint32_t frameIndex;         // which colour/depth plane pair this active slot renders into
+	uint32_t pad[3];
+};
+
+struct Geometry
+{
+	int32_t width, height;
+	int32_t tilesX, tilesY;     // tiles over the whole frame
+	int32_t bandTileY0, bandTileY1; // tile rows rasterised by this context
+	int32_t bandTiles;          // tilesX * (bandTileY1 - bandTileY0)
+	int32_t numFrames;          // ACTIVE frames of this flush (slots into FrameState[])
+};
+
+} // namespace dtr

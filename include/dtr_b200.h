@@ -1,0 +1,168 @@
+/* dtr_b200.h -- C ABI of the B200 (sm_100a) rasterisation back end for DTRenderer's draw path.
+ *
+ * This is the drop-in boundary: one shared library (libdtr_b200.so), `extern "C"`, plain
+ * pointers and sizes, no C++/torch types.  Each draw entry replaces one reference draw call
+ * (reference paths are relative to /root/reference/src):
+ *
+ *   dtr_b200_clear              <- DTRRender_Clear             DTRendererRender.h:98,  .cpp:1793-1815
+ *   dtr_b200_triangle           <- DTRRender_Triangle          DTRendererRender.h:95,  .cpp:1587-1594
+ *   dtr_b200_textured_triangle  <- DTRRender_TexturedTriangle  DTRendererRender.h:96,  .cpp:1358-1365
+ *   dtr_b200_mesh               <- DTRRender_Mesh              DTRendererRender.h:94,  .cpp:1395-1585
+ *   dtr_b200_rectangle          <- DTRRender_Rectangle         DTRendererRender.h:93,  .cpp:415-513
+ *   dtr_b200_bitmap             <- DTRRender_Bitmap            DTRendererRender.h:97,  .cpp:1596-1791
+ *   dtr_b200_line               <- DTRRender_Line              DTRendererRender.h:92,  .cpp:294-356
+ *   dtr_b200_begin_frame        <- per-frame z-buffer reset    DTRenderer.cpp:967-978
+ *   dtr_b200_end_frame          <- hand-back of the DTRRenderBuffer (DTRendererRender.h:14-25)
+ *   dtr_b200_upload_mesh/_texture <- DTRMesh / DTRBitmap as produced by DTRendererAsset
+ *                                    (DTRendererAsset.h:9-42); the loaders stay on the host.
+ *
+ * Semantics.  Draw calls are RECORDED and executed in submission order per frame: the result of
+ * a flush is the reference's single-threaded (`multithread=false`) in-order result -- coverage,
+ * depth decisions and depth values bit-exact, colour bit-exact in practice (tolerance 1/255).
+ * Arguments have the reference's meaning: colours are sRGB in [0,1] (gamma 2.0), transform
+ * rotation is RADIANS for 2D calls and DEGREES about the axis `anchor` for dtr_b200_mesh
+ * (DTRendererRender.cpp:282 vs :1410), buffers are row-major with row 0 at the bottom, colour
+ * pixels are 0x00RRGGBB and depth is f32 with larger = nearer, reset value -FLT_MAX.
+ * Inputs the reference would assert on (w != 1, uv > 1, colours outside [0,1], w_clip <= 0)
+ * are undefined here too.
+ *
+ * Errors.  Every call returns 0 on success or a negative dtr_b200_status; NULL/invalid
+ * arguments that the reference silently ignores (DTRendererRender.cpp:128,420,1402,1601,1796)
+ * return DTR_B200_OK without drawing.  There is NO CPU fallback: without a CUDA device
+ * dtr_b200_create fails with DTR_B200_ERR_CUDA.
+ *
+ * Threading.  One host thread per context; all work is enqueued on the context's CUDA stream.
+ */
+#ifndef DTR_B200_H
+#define DTR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dtr_b200_ctx dtr_b200_ctx;
+
+typedef enum dtr_b200_status
+{
+	DTR_B200_OK           = 0,
+	DTR_B200_ERR_ARG      = -1, /* out-of-range id / frame / size */
+	DTR_B200_ERR_CUDA     = -2, /* CUDA runtime error, see dtr_b200_last_error */
+	DTR_B200_ERR_NOMEM    = -3,
+	DTR_B200_ERR_OVERFLOW = -4, /* more than 2^31 primitives / list entries in one flush */
+} dtr_b200_status;
+
+/* Layout-compatible with DTRRenderTransform (DTRendererRender.h:28-33): 7 floats. */
+typedef struct dtr_b200_transform
+{
+	float rotation;
+	float anchor[3];
+	float scale[3];
+} dtr_b200_transform;
+
+/* DTRRenderShadingMode (DTRendererRender.h:63-68) */
+enum
+{
+	DTR_B200_SHADE_FULLBRIGHT = 0,
+	DTR_B200_SHADE_FLAT       = 1,
+	DTR_B200_SHADE_GOURAUD    = 2,
+};
+
+/* Layout-compatible with DTRRenderLight (DTRendererRender.h:72-77). */
+typedef struct dtr_b200_light
+{
+	int32_t mode;
+	float   vector[3];
+	float   color[4];
+} dtr_b200_light;
+
+/* DTRMesh flattened (DTRendererAsset.h:16-41): the per-face index arrays become one
+ * i32[numFaces*9] = {v0,v1,v2, t0,t1,t2, n0,n1,n2}. */
+typedef struct dtr_b200_mesh_desc
+{
+	const float   *vertexes; /* f32[numVertexes*4], w must be 1 */
+	uint32_t       numVertexes;
+	const float   *texUV;    /* f32[numTexUV*3] */
+	uint32_t       numTexUV;
+	const float   *normals;  /* f32[numNormals*3] */
+	uint32_t       numNormals;
+	const int32_t *faces;    /* i32[numFaces*9] */
+	uint32_t       numFaces;
+} dtr_b200_mesh_desc;
+
+typedef struct dtr_b200_stats
+{
+	uint64_t setPixels;    /* fragments that passed coverage and the z-test == DTRDebugCounter_SetPixels */
+	uint64_t triangles;    /* triangles submitted == DTRDebugCounter_RenderTriangle */
+	uint64_t primitives;   /* primitives in the last flush */
+	uint64_t listEntries;  /* (primitive, tile) pairs in the last flush */
+	uint64_t kernelLaunches; /* kernels launched by this context so far */
+} dtr_b200_stats;
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* numFrames colour+depth targets of width x height live in HBM; draw calls go to the current
+ * target (dtr_b200_set_target), so one flush can render a whole batch of frames/viewpoints. */
+int         dtr_b200_create(int device, int width, int height, int numFrames, dtr_b200_ctx **out);
+void        dtr_b200_destroy(dtr_b200_ctx *ctx);
+const char *dtr_b200_last_error(const dtr_b200_ctx *ctx); /* ctx may be NULL: last create error */
+const char *dtr_b200_version(void);
+/* Use an existing cudaStream_t (e.g. the caller's current stream) instead of the context's own. */
+int         dtr_b200_set_stream(dtr_b200_ctx *ctx, void *cudaStream);
+/* Sort-first band split: only rows [y0,y1) are rasterised by this context (tile aligned: both
+ * multiples of 32 or y1 == height).  Default is the whole frame. */
+int         dtr_b200_set_band(dtr_b200_ctx *ctx, int y0, int y1);
+
+/* ---- assets (device resident until destroy) ----------------------------------------------- */
+int dtr_b200_upload_texture(dtr_b200_ctx *ctx, const uint8_t *texels, int width, int height,
+                            int bytesPerPixel /* must be 4 */, int *texId);
+int dtr_b200_upload_mesh(dtr_b200_ctx *ctx, const dtr_b200_mesh_desc *mesh, int texId, int *meshId);
+
+/* ---- frame -------------------------------------------------------------------------------- */
+int dtr_b200_set_target(dtr_b200_ctx *ctx, int frame);
+/* Start a frame on `frame`: depth is reset to -FLT_MAX (hostZ == NULL) or uploaded; colour is
+ * kept from the previous frame (hostColor == NULL, as the reference's platform buffer is) or
+ * uploaded.  Host buffers are W*H elements, caller owned, only read here. */
+int dtr_b200_begin_frame(dtr_b200_ctx *ctx, int frame, const uint32_t *hostColor, const float *hostZ);
+/* Execute everything recorded so far (asynchronous on the context's stream). */
+int dtr_b200_flush(dtr_b200_ctx *ctx);
+/* Re-execute the last flushed command list from its device-resident copy (no host->device
+ * traffic): every frame it touched is re-initialised the way it was before that flush. */
+int dtr_b200_replay(dtr_b200_ctx *ctx);
+int dtr_b200_sync(dtr_b200_ctx *ctx);
+/* Flush, then copy the frame back (either pointer may be NULL) and wait for it. */
+int dtr_b200_end_frame(dtr_b200_ctx *ctx, int frame, uint32_t *hostColor, float *hostZ);
+/* Device pointers of a frame's planes (u32[W*H], f32[W*H]) for zero-copy consumers
+ * (NCCL / peer access / torch views). */
+int dtr_b200_frame_device_ptrs(dtr_b200_ctx *ctx, int frame, void **color, void **z);
+int dtr_b200_get_stats(dtr_b200_ctx *ctx, dtr_b200_stats *out); /* syncs */
+int dtr_b200_reset_stats(dtr_b200_ctx *ctx);
+
+/* ---- draw calls --------------------------------------------------------------------------- */
+int dtr_b200_clear(dtr_b200_ctx *ctx, const float rgb[3]);
+int dtr_b200_triangle(dtr_b200_ctx *ctx, const float p1[3], const float p2[3], const float p3[3],
+                      const float color[4], const dtr_b200_transform *transform);
+/* n triangles sharing one transform, submitted in order: p f32[n*9], color f32[n*4] */
+int dtr_b200_triangles(dtr_b200_ctx *ctx, int n, const float *p, const float *color,
+                       const dtr_b200_transform *transform);
+int dtr_b200_textured_triangle(dtr_b200_ctx *ctx, const float p1[3], const float p2[3],
+                               const float p3[3], const float uv1[2], const float uv2[2],
+                               const float uv3[2], int texId /* <0: untextured */,
+                               const float color[4], const dtr_b200_transform *transform);
+int dtr_b200_mesh(dtr_b200_ctx *ctx, int meshId, const dtr_b200_light *light, const float pos[3],
+                  const dtr_b200_transform *transform);
+/* nViews DTRRender_Mesh calls, view i drawn into frame firstFrame + i (frame/viewpoint
+ * parallel batch): pos f32[nViews*3], transforms[nViews]. */
+int dtr_b200_mesh_views(dtr_b200_ctx *ctx, int meshId, const dtr_b200_light *light, int nViews,
+                        const float *pos, const dtr_b200_transform *transforms, int firstFrame);
+int dtr_b200_rectangle(dtr_b200_ctx *ctx, const float min[2], const float max[2],
+                       const float color[4], const dtr_b200_transform *transform);
+int dtr_b200_bitmap(dtr_b200_ctx *ctx, int texId, const float pos[2],
+                    const dtr_b200_transform *transform, const float color[4]);
+int dtr_b200_line(dtr_b200_ctx *ctx, const int32_t a[2], const int32_t b[2], const float color[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DTR_B200_H */
