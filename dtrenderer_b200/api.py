@@ -38,7 +38,7 @@ class MeshDesc(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("setPixels", C.c_uint64), ("triangles", C.c_uint64), ("primitives", C.c_uint64),
-                ("listEntries", C.c_uint64), ("kernelLaunches", C.c_uint64)]
+                ("listEntries", C.c_uint64), ("kernelLaunches", C.c_uint64), ("uploadBytes", C.c_uint64)]
 
 
 # every symbol include/dtr_b200.h declares: (name, restype, argtypes)
@@ -59,9 +59,13 @@ SYMBOLS = [
     ("dtr_b200_replay", C.c_int, [C.c_void_p]),
     ("dtr_b200_sync", C.c_int, [C.c_void_p]),
     ("dtr_b200_end_frame", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    ("dtr_b200_read_frames", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     ("dtr_b200_frame_device_ptrs", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     ("dtr_b200_get_stats", C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     ("dtr_b200_reset_stats", C.c_int, [C.c_void_p]),
+    ("dtr_b200_set_profiling", C.c_int, [C.c_void_p, C.c_int]),
+    ("dtr_b200_get_stage_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float * 4), C.POINTER(C.c_int)]),
+    ("dtr_b200_reset_stage_ms", C.c_int, [C.c_void_p]),
     ("dtr_b200_clear", C.c_int, [C.c_void_p, _f]),
     ("dtr_b200_triangle", C.c_int, [C.c_void_p, _f, _f, _f, _f, _T]),
     ("dtr_b200_triangles", C.c_int, [C.c_void_p, C.c_int, _f, _f, _T]),
@@ -207,6 +211,11 @@ class Renderer:
         self._ck(self.lib.dtr_b200_end_frame(self.ctx, frame, C.c_void_p(color_ptr),
                                              C.c_void_p(z_ptr) if z_ptr else None))
 
+    def read_frames_ptr(self, first, n, color_ptr, z_ptr=None):
+        """Flush and copy n consecutive frames into caller-owned host memory (raw addresses)."""
+        self._ck(self.lib.dtr_b200_read_frames(self.ctx, first, n, C.c_void_p(color_ptr),
+                                               C.c_void_p(z_ptr) if z_ptr else None))
+
     def frame_device_ptrs(self, frame=0):
         c, z = C.c_void_p(), C.c_void_p()
         self._ck(self.lib.dtr_b200_frame_device_ptrs(self.ctx, frame, C.byref(c), C.byref(z)))
@@ -219,6 +228,18 @@ class Renderer:
 
     def reset_stats(self):
         self._ck(self.lib.dtr_b200_reset_stats(self.ctx))
+
+    def set_profiling(self, on=True):
+        self._ck(self.lib.dtr_b200_set_profiling(self.ctx, int(on)))
+
+    def reset_stage_ms(self):
+        self._ck(self.lib.dtr_b200_reset_stage_ms(self.ctx))
+
+    def stage_ms(self):
+        """Summed device ms of (setup, scan, bin, raster) and the number of pipelines timed."""
+        ms, runs = (C.c_float * 4)(), C.c_int(0)
+        self._ck(self.lib.dtr_b200_get_stage_ms(self.ctx, C.byref(ms), C.byref(runs)))
+        return dict(setup=ms[0], scan=ms[1], bin=ms[2], raster=ms[3]), runs.value
 
     def counters(self):
         s = self.stats()

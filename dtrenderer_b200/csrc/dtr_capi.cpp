@@ -78,11 +78,15 @@ struct dtr_b200_ctx
 
 	std::vector<MeshAsset> meshes;
 	std::vector<TexDesc>   textures;
+	std::vector<uint8_t>   texIsWhite; // every texel 0xFFFFFFFF: sampling multiplies by exactly 1.0f
 	DevBuf                 dTextures;
 
 	DevBuf dCmd, dPayload, dPrims, dBounds, dTileCount, dTileOffset, dLists;
 	unsigned long long *dSetPixels = nullptr; // [0] = SetPixel count, [1] = list total of last scan
-	uint64_t            triangles = 0, launches = 0;
+	uint64_t            triangles = 0, launches = 0, uploadBytes = 0;
+	bool                     profiling = false;
+	std::vector<cudaEvent_t> events;     // 5 per profiled pipeline
+	std::vector<cudaEvent_t> eventPool;  // recycled
 
 	// last flush, for replay
 	struct
@@ -217,7 +221,7 @@ int record_tris(dtr_b200_ctx *c, int n, const float *p, const float *color, cons
 	r.relocate[1]    = true;
 	r.payload[2]     = offUV;
 	r.relocate[2]    = (uv != nullptr);
-	r.item.texId     = texId;
+	r.item.texId     = (texId >= 0 && c->texIsWhite[texId]) ? -1 : texId;
 	r.item.lightMode = DTR_B200_SHADE_FULLBRIGHT; // NullRenderLightInternal (:1352-1356)
 	Basis2 b         = make_basis(t->rotation, t->scale[0], t->scale[1]);
 	r.item.xAxis[0] = b.xAxis[0]; r.item.xAxis[1] = b.xAxis[1];
@@ -225,6 +229,21 @@ int record_tris(dtr_b200_ctx *c, int n, const float *p, const float *color, cons
 	r.item.anchor[0] = t->anchor[0];
 	r.item.anchor[1] = t->anchor[1];
 	c->triangles += (uint64_t)n;
+	return 0;
+}
+
+int mark(dtr_b200_ctx *c)
+{
+	if (!c->profiling || c->events.size() >= 5 * 8192) return 0;
+	cudaEvent_t e;
+	if (!c->eventPool.empty())
+	{
+		e = c->eventPool.back();
+		c->eventPool.pop_back();
+	}
+	else CU(cudaEventCreate(&e));
+	CU(cudaEventRecord(e, c->stream));
+	c->events.push_back(e);
 	return 0;
 }
 
@@ -243,6 +262,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	if ((rc = ensure_dev(c, c->dBounds, sizeof(PrimBounds) * (size_t)std::max(numPrims, 1u)))) return rc;
 
 	CU(cudaMemsetAsync(c->dTileCount.p, 0, sizeof(uint32_t) * (size_t)numTiles, c->stream));
+	if ((rc = mark(c))) return rc;
 	if (numPrims)
 	{
 		SetupParams S;
@@ -256,9 +276,11 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 		launch_setup(S, c->stream);
 		c->launches++;
 	}
+	if ((rc = mark(c))) return rc;
 	launch_scan((const uint32_t *)c->dTileCount.p, (uint32_t *)c->dTileOffset.p, numTiles, c->dSetPixels + 1,
 	            c->stream);
 	c->launches++;
+	if ((rc = mark(c))) return rc;
 
 	uint64_t total = c->last.listTotal;
 	if (!replay)
@@ -284,6 +306,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 		launch_bin(B, c->stream);
 		c->launches++;
 	}
+	if ((rc = mark(c))) return rc;
 
 	RasterParams R;
 	R.color      = c->dColor;
@@ -299,6 +322,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	R.g          = g;
 	launch_raster(R, c->stream);
 	c->launches++;
+	if ((rc = mark(c))) return rc;
 	CU(cudaGetLastError());
 
 	c->last.valid     = true;
@@ -370,6 +394,7 @@ int do_flush(dtr_b200_ctx *c)
 	for (uint32_t s = 0; s < numActive; s++)
 		if (c->frames[active[s]].recorded == 0) fs[s].primBegin = fs[s].primEnd = 0;
 
+	c->uploadBytes = cmdBytes + c->payloadUsed;
 	CU(cudaMemcpyAsync(c->dCmd.p, c->staging, cmdBytes, cudaMemcpyHostToDevice, c->stream));
 	if (c->payloadUsed)
 		CU(cudaMemcpyAsync(c->dPayload.p, c->payload, c->payloadUsed, cudaMemcpyHostToDevice, c->stream));
@@ -459,6 +484,8 @@ void dtr_b200_destroy(dtr_b200_ctx *c)
 	cudaFree(c->dSetPixels);
 	if (c->payload) cudaFreeHost(c->payload);
 	if (c->staging) cudaFreeHost(c->staging);
+	for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+	for (cudaEvent_t e : c->eventPool) cudaEventDestroy(e);
 	if (c->ownStream) cudaStreamDestroy(c->ownStream);
 	delete c;
 }
@@ -498,6 +525,22 @@ int dtr_b200_upload_texture(dtr_b200_ctx *c, const uint8_t *texels, int width, i
 	CU(cudaMalloc((void **)&d, bytes));
 	CU(cudaMemcpy(d, texels, bytes, cudaMemcpyHostToDevice));
 	c->textures.push_back(TexDesc{d, width, height});
+	{
+		// 255 * (1/255.0f) == 1.0f and 1.0f^2 == 1.0f in fp32, so an all-white opaque texture leaves
+		// every channel bit-identical: triangles using it skip the fetch (DTRRender_Mesh always
+		// samples mesh->tex, so "untextured" meshes carry exactly such a 1x1 texture)
+		bool           white = true;
+		const uint32_t *t32  = reinterpret_cast<const uint32_t *>(texels);
+		if (((uintptr_t)texels & 3) == 0)
+		{
+			for (size_t i = 0; i < (size_t)width * height && white; i++) white = (t32[i] == 0xFFFFFFFFu);
+		}
+		else
+		{
+			for (size_t i = 0; i < bytes && white; i++) white = (texels[i] == 0xFF);
+		}
+		c->texIsWhite.push_back(white ? 1 : 0);
+	}
 	CU(cudaStreamSynchronize(c->stream)); // the old table may be in use
 	int rc = ensure_dev(c, c->dTextures, sizeof(TexDesc) * std::max<size_t>(c->textures.capacity(), 16));
 	if (rc) return rc;
@@ -604,6 +647,22 @@ int dtr_b200_end_frame(dtr_b200_ctx *c, int frame, uint32_t *hostColor, float *h
 	return DTR_B200_OK;
 }
 
+int dtr_b200_read_frames(dtr_b200_ctx *c, int first, int n, uint32_t *hostColor, float *hostZ)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (n <= 0 || !valid_frame(c, first) || !valid_frame(c, first + n - 1)) return fail(c, DTR_B200_ERR_ARG, "frame range out of bounds");
+	CU(cudaSetDevice(c->device));
+	int rc = do_flush(c);
+	if (rc) return rc;
+	size_t plane = (size_t)c->width * c->height;
+	if (hostColor)
+		CU(cudaMemcpyAsync(hostColor, c->dColor + plane * first, plane * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	if (hostZ)
+		CU(cudaMemcpyAsync(hostZ, c->dDepth + plane * first, plane * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return DTR_B200_OK;
+}
+
 int dtr_b200_frame_device_ptrs(dtr_b200_ctx *c, int frame, void **color, void **z)
 {
 	if (!c) return DTR_B200_ERR_ARG;
@@ -626,6 +685,41 @@ int dtr_b200_get_stats(dtr_b200_ctx *c, dtr_b200_stats *out)
 	out->primitives     = c->last.numPrims;
 	out->listEntries    = c->last.listTotal;
 	out->kernelLaunches = c->launches;
+	out->uploadBytes    = c->uploadBytes;
+	return DTR_B200_OK;
+}
+
+int dtr_b200_set_profiling(dtr_b200_ctx *c, int enable)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	c->profiling = enable != 0;
+	return DTR_B200_OK;
+}
+
+int dtr_b200_reset_stage_ms(dtr_b200_ctx *c)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	for (cudaEvent_t e : c->events) c->eventPool.push_back(e);
+	c->events.clear();
+	return DTR_B200_OK;
+}
+
+int dtr_b200_get_stage_ms(dtr_b200_ctx *c, float ms[4], int *runs)
+{
+	if (!c || !ms || !runs) return DTR_B200_ERR_ARG;
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	ms[0] = ms[1] = ms[2] = ms[3] = 0.0f;
+	*runs = (int)(c->events.size() / 5);
+	for (int r = 0; r < *runs; r++)
+		for (int s = 0; s < 4; s++)
+		{
+			float t = 0.0f;
+			CU(cudaEventElapsedTime(&t, c->events[5 * r + s], c->events[5 * r + s + 1]));
+			ms[s] += t;
+		}
 	return DTR_B200_OK;
 }
 
@@ -707,7 +801,8 @@ int dtr_b200_mesh_views(dtr_b200_ctx *c, int meshId, const dtr_b200_light *light
 		const dtr_b200_transform &t = transforms[v];
 		Mat4     M = mesh_matrix(c->width, c->height, pos + 3 * v, t.rotation, t.anchor, t.scale);
 		RecItem &r = new_item(c, ITEM_MESH, (uint32_t)(firstFrame + v), m.numFaces);
-		r.item.texId     = m.texId; // DTRRender_Mesh always samples mesh->tex (:1563-1564)
+		// DTRRender_Mesh always samples mesh->tex (:1563-1564); an all-white one is a no-op
+		r.item.texId     = (m.texId >= 0 && c->texIsWhite[m.texId]) ? -1 : m.texId;
 		r.item.lightMode = (uint32_t)light->mode;
 		r.item.ptr[0]    = (uint64_t)m.vertexes;
 		r.item.ptr[1]    = (uint64_t)m.texUV;

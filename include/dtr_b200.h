@@ -99,6 +99,7 @@ typedef struct dtr_b200_stats
 	uint64_t primitives;   /* primitives in the last flush */
 	uint64_t listEntries;  /* (primitive, tile) pairs in the last flush */
 	uint64_t kernelLaunches; /* kernels launched by this context so far */
+	uint64_t uploadBytes;  /* host->device bytes of the last flush (command block + payload) */
 } dtr_b200_stats;
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -133,11 +134,21 @@ int dtr_b200_replay(dtr_b200_ctx *ctx);
 int dtr_b200_sync(dtr_b200_ctx *ctx);
 /* Flush, then copy the frame back (either pointer may be NULL) and wait for it. */
 int dtr_b200_end_frame(dtr_b200_ctx *ctx, int frame, uint32_t *hostColor, float *hostZ);
+/* Flush, then copy n consecutive frames back in one transfer per plane (either pointer may be
+ * NULL): hostColor u32[n*W*H], hostZ f32[n*W*H]; waits for completion. */
+int dtr_b200_read_frames(dtr_b200_ctx *ctx, int firstFrame, int n, uint32_t *hostColor, float *hostZ);
 /* Device pointers of a frame's planes (u32[W*H], f32[W*H]) for zero-copy consumers
  * (NCCL / peer access / torch views). */
 int dtr_b200_frame_device_ptrs(dtr_b200_ctx *ctx, int frame, void **color, void **z);
 int dtr_b200_get_stats(dtr_b200_ctx *ctx, dtr_b200_stats *out); /* syncs */
 int dtr_b200_reset_stats(dtr_b200_ctx *ctx);
+/* Per-stage device timing with CUDA events on the context's stream (the ncu/nsys replacement of
+ * the reference's rdtsc region counters, DTRendererDebug.h:42-78).  While enabled, every
+ * flush/replay records 5 events; dtr_b200_get_stage_ms syncs and returns the SUMS in ms of
+ * {setup, scan, bin, raster} over the pipelines run since the last reset, and their number. */
+int dtr_b200_set_profiling(dtr_b200_ctx *ctx, int enable);
+int dtr_b200_get_stage_ms(dtr_b200_ctx *ctx, float ms[4], int *runs);
+int dtr_b200_reset_stage_ms(dtr_b200_ctx *ctx);
 
 /* ---- draw calls --------------------------------------------------------------------------- */
 int dtr_b200_clear(dtr_b200_ctx *ctx, const float rgb[3]);
