@@ -82,7 +82,7 @@ struct dtr_b200_ctx
 	DevBuf                 dTextures;
 
 	DevBuf dCmd, dPayload, dPrims, dBounds, dTileCount, dTileOffset, dLists;
-	unsigned long long *dSetPixels = nullptr; // [0] = SetPixel count, [1] = list total of last scan
+	unsigned long long *dSetPixels = nullptr; // [0] SetPixel count, [1] list total of last scan, [2] work counter
 	uint64_t            triangles = 0, launches = 0, uploadBytes = 0;
 	bool                     profiling = false;
 	std::vector<cudaEvent_t> events;     // 5 per profiled pipeline
@@ -278,7 +278,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	}
 	if ((rc = mark(c))) return rc;
 	launch_scan((const uint32_t *)c->dTileCount.p, (uint32_t *)c->dTileOffset.p, numTiles, c->dSetPixels + 1,
-	            c->stream);
+	            (uint32_t *)(c->dSetPixels + 2), c->stream);
 	c->launches++;
 	if ((rc = mark(c))) return rc;
 
@@ -319,6 +319,9 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	R.lists      = (const uint32_t *)c->dLists.p;
 	R.textures   = (const TexDesc *)c->dTextures.p;
 	R.setPixels  = c->dSetPixels;
+	R.workCounter    = (uint32_t *)(c->dSetPixels + 2);
+	R.numItems       = 0;
+	R.regionsPerItem = 0;
 	R.g          = g;
 	launch_raster(R, c->stream);
 	c->launches++;
@@ -448,9 +451,9 @@ int dtr_b200_create(int device, int width, int height, int numFrames, dtr_b200_c
 	if ((e = cudaStreamCreateWithFlags(&n->ownStream, cudaStreamNonBlocking)) != cudaSuccess ||
 	    (e = cudaMalloc((void **)&n->dColor, plane * numFrames * sizeof(uint32_t))) != cudaSuccess ||
 	    (e = cudaMalloc((void **)&n->dDepth, plane * numFrames * sizeof(float))) != cudaSuccess ||
-	    (e = cudaMalloc((void **)&n->dSetPixels, 2 * sizeof(unsigned long long))) != cudaSuccess ||
+	    (e = cudaMalloc((void **)&n->dSetPixels, 4 * sizeof(unsigned long long))) != cudaSuccess ||
 	    (e = cudaMemset(n->dColor, 0, plane * numFrames * sizeof(uint32_t))) != cudaSuccess ||
-	    (e = cudaMemset(n->dSetPixels, 0, 2 * sizeof(unsigned long long))) != cudaSuccess)
+	    (e = cudaMemset(n->dSetPixels, 0, 4 * sizeof(unsigned long long))) != cudaSuccess)
 	{
 		fail(nullptr, DTR_B200_ERR_CUDA, "allocating frame targets", e);
 		dtr_b200_destroy(n);

@@ -41,11 +41,15 @@ struct RasterParams
 	const uint32_t     *lists;
 	const TexDesc      *textures;
 	unsigned long long *setPixels;
+	uint32_t           *workCounter;    // zeroed by scan_kernel; items handed out by atomicAdd
+	uint32_t            numItems;       // filled by launch_raster
+	uint32_t            regionsPerItem; // 8 (a whole tile per pull) or 1
 	Geometry            g;
 };
 
 void launch_setup(const SetupParams &P, cudaStream_t s);
-void launch_scan(const uint32_t *counts, uint32_t *offsets, uint32_t n, unsigned long long *total, cudaStream_t s);
+void launch_scan(const uint32_t *counts, uint32_t *offsets, uint32_t n, unsigned long long *total,
+                 uint32_t *workCounter, cudaStream_t s);
 void launch_bin(const BinParams &P, cudaStream_t s);
 void launch_raster(const RasterParams &P, cudaStream_t s);
 
