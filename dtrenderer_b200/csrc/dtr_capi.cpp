@@ -81,8 +81,8 @@ struct dtr_b200_ctx
 	std::vector<uint8_t>   texIsWhite; // every texel 0xFFFFFFFF: sampling multiplies by exactly 1.0f
 	DevBuf                 dTextures;
 
-	DevBuf dCmd, dPayload, dPrims, dBounds, dTileCount, dTileOffset, dLists;
-	unsigned long long *dSetPixels = nullptr; // [0] SetPixel count, [1] list total of last scan, [2] work counter
+	DevBuf dCmd, dPayload, dPrims, dBounds, dTileCount, dTileOffset, dLists, dCoarseOffset, dCoarseLists;
+	unsigned long long *dSetPixels = nullptr; // [0] SetPixel count, [1] list total, [2] coarse list total, [3] work counter
 	uint64_t            triangles = 0, launches = 0, uploadBytes = 0;
 	bool                     profiling = false;
 	std::vector<cudaEvent_t> events;     // 5 per profiled pipeline
@@ -92,8 +92,8 @@ struct dtr_b200_ctx
 	struct
 	{
 		bool     valid = false;
-		uint32_t numActive = 0, numItems = 0, numPrims = 0;
-		uint64_t listTotal = 0, triangles = 0;
+		uint32_t numActive = 0, numItems = 0, numPrims = 0, maxFramePrims = 0;
+		uint64_t listTotal = 0, coarseTotal = 0, triangles = 0;
 		Geometry g{};
 	} last;
 
@@ -247,62 +247,88 @@ int mark(dtr_b200_ctx *c)
 	return 0;
 }
 
-int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_t numPrims, bool replay)
+int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_t numPrims, uint32_t maxFramePrims,
+                 bool replay)
 {
 	Geometry g   = c->geom;
 	g.numFrames  = (int32_t)numActive;
-	uint32_t numTiles = numActive * (uint32_t)g.bandTiles;
+	g.coarseX = g.coarseY = g.coarseBins = g.coarseSegs = 0;
+	if (maxFramePrims >= (uint32_t)TWO_LEVEL_MIN_PRIMS)
+	{
+		g.coarseX    = (g.tilesX + COARSE_TILES - 1) / COARSE_TILES;
+		g.coarseY    = (g.bandTileY1 - g.bandTileY0 + COARSE_TILES - 1) / COARSE_TILES;
+		g.coarseBins = g.coarseX * g.coarseY;
+		g.coarseSegs = (int32_t)((maxFramePrims + COARSE_SEG - 1) / COARSE_SEG);
+	}
+	uint32_t numTiles  = numActive * (uint32_t)g.bandTiles;
+	uint32_t numCoarse = numActive * (uint32_t)g.coarseBins * (uint32_t)g.coarseSegs;
 	const FrameState *dFrames = (const FrameState *)c->dCmd.p;
 	const DrawItem   *dItems  = (const DrawItem *)((const uint8_t *)c->dCmd.p + sizeof(FrameState) * numActive);
 
 	int rc;
-	if ((rc = ensure_dev(c, c->dTileCount, sizeof(uint32_t) * (size_t)numTiles))) return rc;
-	if ((rc = ensure_dev(c, c->dTileOffset, sizeof(uint32_t) * (size_t)numTiles))) return rc;
+	// tile counts and coarse counts share one buffer so that one memset clears both
+	if ((rc = ensure_dev(c, c->dTileCount, sizeof(uint32_t) * ((size_t)numTiles + numCoarse)))) return rc;
+	if ((rc = ensure_dev(c, c->dTileOffset, sizeof(uint32_t) * ((size_t)numTiles + 1)))) return rc;
+	if ((rc = ensure_dev(c, c->dCoarseOffset, sizeof(uint32_t) * ((size_t)numCoarse + 1)))) return rc;
 	if ((rc = ensure_dev(c, c->dPrims, sizeof(PrimRecord) * (size_t)std::max(numPrims, 1u)))) return rc;
 	if ((rc = ensure_dev(c, c->dBounds, sizeof(PrimBounds) * (size_t)std::max(numPrims, 1u)))) return rc;
+	uint32_t *dTileCount = (uint32_t *)c->dTileCount.p, *dCoarseCount = dTileCount + numTiles;
 
-	CU(cudaMemsetAsync(c->dTileCount.p, 0, sizeof(uint32_t) * (size_t)numTiles, c->stream));
+	CU(cudaMemsetAsync(dTileCount, 0, sizeof(uint32_t) * ((size_t)numTiles + numCoarse), c->stream));
 	if ((rc = mark(c))) return rc;
 	if (numPrims)
 	{
 		SetupParams S;
-		S.items     = dItems;
-		S.numItems  = (int)numItems;
-		S.numPrims  = numPrims;
-		S.prims     = (PrimRecord *)c->dPrims.p;
-		S.bounds    = (PrimBounds *)c->dBounds.p;
-		S.tileCount = (uint32_t *)c->dTileCount.p;
-		S.g         = g;
+		S.items       = dItems;
+		S.numItems    = (int)numItems;
+		S.numPrims    = numPrims;
+		S.prims       = (PrimRecord *)c->dPrims.p;
+		S.bounds      = (PrimBounds *)c->dBounds.p;
+		S.tileCount   = dTileCount;
+		S.coarseCount = dCoarseCount;
+		S.frames      = dFrames;
+		S.g           = g;
 		launch_setup(S, c->stream);
 		c->launches++;
 	}
 	if ((rc = mark(c))) return rc;
-	launch_scan((const uint32_t *)c->dTileCount.p, (uint32_t *)c->dTileOffset.p, numTiles, c->dSetPixels + 1,
-	            (uint32_t *)(c->dSetPixels + 2), c->stream);
+	launch_scan(dTileCount, (uint32_t *)c->dTileOffset.p, numTiles, dCoarseCount, (uint32_t *)c->dCoarseOffset.p,
+	            numCoarse, c->dSetPixels + 1, (uint32_t *)(c->dSetPixels + 3), c->stream);
 	c->launches++;
 	if ((rc = mark(c))) return rc;
 
-	uint64_t total = c->last.listTotal;
+	uint64_t total = c->last.listTotal, coarseTotal = c->last.coarseTotal;
 	if (!replay)
 	{
-		unsigned long long t = 0;
-		CU(cudaMemcpyAsync(&t, c->dSetPixels + 1, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
+		unsigned long long t[2] = {0, 0};
+		CU(cudaMemcpyAsync(t, c->dSetPixels + 1, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
 		CU(cudaStreamSynchronize(c->stream));
-		total = t;
-		if (total >= (1ull << 31)) return fail(c, DTR_B200_ERR_OVERFLOW, "more than 2^31 (primitive, tile) pairs in one flush");
+		total       = t[0];
+		coarseTotal = numCoarse ? t[1] : 0;
+		if (total >= (1ull << 31) || coarseTotal >= (1ull << 31))
+			return fail(c, DTR_B200_ERR_OVERFLOW, "more than 2^31 (primitive, tile) pairs in one flush");
 		if ((rc = ensure_dev(c, c->dLists, sizeof(uint32_t) * (size_t)std::max<uint64_t>(total, 1)))) return rc;
+		if ((rc = ensure_dev(c, c->dCoarseLists, sizeof(uint32_t) * (size_t)std::max<uint64_t>(coarseTotal, 1)))) return rc;
 	}
 
 	if (numPrims && total)
 	{
 		BinParams B;
-		B.bounds       = (const PrimBounds *)c->dBounds.p;
-		B.frames       = dFrames;
-		B.tileCount    = (const uint32_t *)c->dTileCount.p;
-		B.tileOffset   = (const uint32_t *)c->dTileOffset.p;
-		B.lists        = (uint32_t *)c->dLists.p;
-		B.listCapacity = (uint32_t)(c->dLists.cap / sizeof(uint32_t));
-		B.g            = g;
+		B.bounds         = (const PrimBounds *)c->dBounds.p;
+		B.frames         = dFrames;
+		B.tileCount      = dTileCount;
+		B.tileOffset     = (const uint32_t *)c->dTileOffset.p;
+		B.lists          = (uint32_t *)c->dLists.p;
+		B.listCapacity   = (uint32_t)(c->dLists.cap / sizeof(uint32_t));
+		B.coarseOffset   = (const uint32_t *)c->dCoarseOffset.p;
+		B.coarseLists    = (uint32_t *)c->dCoarseLists.p;
+		B.coarseCapacity = (uint32_t)(c->dCoarseLists.cap / sizeof(uint32_t));
+		B.g              = g;
+		if (numCoarse)
+		{
+			launch_bin_coarse(B, c->stream);
+			c->launches++;
+		}
 		launch_bin(B, c->stream);
 		c->launches++;
 	}
@@ -314,12 +340,12 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	R.frames     = dFrames;
 	R.prims      = (const PrimRecord *)c->dPrims.p;
 	R.bounds     = (const PrimBounds *)c->dBounds.p;
-	R.tileCount  = (const uint32_t *)c->dTileCount.p;
+	R.tileCount  = dTileCount;
 	R.tileOffset = (const uint32_t *)c->dTileOffset.p;
 	R.lists      = (const uint32_t *)c->dLists.p;
 	R.textures   = (const TexDesc *)c->dTextures.p;
 	R.setPixels  = c->dSetPixels;
-	R.workCounter    = (uint32_t *)(c->dSetPixels + 2);
+	R.workCounter    = (uint32_t *)(c->dSetPixels + 3);
 	R.numItems       = 0;
 	R.regionsPerItem = 0;
 	R.g          = g;
@@ -333,6 +359,8 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	c->last.numItems  = numItems;
 	c->last.numPrims  = numPrims;
 	c->last.listTotal = total;
+	c->last.coarseTotal   = coarseTotal;
+	c->last.maxFramePrims = maxFramePrims;
 	c->last.g         = g;
 	return 0;
 }
@@ -402,7 +430,9 @@ int do_flush(dtr_b200_ctx *c)
 	if (c->payloadUsed)
 		CU(cudaMemcpyAsync(c->dPayload.p, c->payload, c->payloadUsed, cudaMemcpyHostToDevice, c->stream));
 
-	rc = run_pipeline(c, numActive, numItems, (uint32_t)prim, false);
+	uint32_t maxFramePrims = 0;
+	for (uint32_t s2 = 0; s2 < numActive; s2++) maxFramePrims = std::max(maxFramePrims, fs[s2].primEnd - fs[s2].primBegin);
+	rc = run_pipeline(c, numActive, numItems, (uint32_t)prim, maxFramePrims, false);
 	// the host copies were consumed (run_pipeline synchronises before binning)
 	for (uint32_t s = 0; s < numActive; s++)
 	{
@@ -480,7 +510,8 @@ void dtr_b200_destroy(dtr_b200_ctx *c)
 		cudaFree(m.faces);
 	}
 	for (auto &t : c->textures) cudaFree((void *)t.texels);
-	DevBuf *bufs[] = {&c->dTextures, &c->dCmd, &c->dPayload, &c->dPrims, &c->dBounds, &c->dTileCount, &c->dTileOffset, &c->dLists};
+	DevBuf *bufs[] = {&c->dTextures, &c->dCmd, &c->dPayload, &c->dPrims, &c->dBounds, &c->dTileCount, &c->dTileOffset, &c->dLists,
+	                  &c->dCoarseOffset, &c->dCoarseLists};
 	for (DevBuf *b : bufs) cudaFree(b->p);
 	cudaFree(c->dColor);
 	cudaFree(c->dDepth);
@@ -624,7 +655,7 @@ int dtr_b200_replay(dtr_b200_ctx *c)
 	if (!c->last.valid) return fail(c, DTR_B200_ERR_ARG, "nothing to replay");
 	if (!c->rec.empty()) return fail(c, DTR_B200_ERR_ARG, "replay with unflushed draw calls pending");
 	CU(cudaSetDevice(c->device));
-	return run_pipeline(c, c->last.numActive, c->last.numItems, c->last.numPrims, true);
+	return run_pipeline(c, c->last.numActive, c->last.numItems, c->last.numPrims, c->last.maxFramePrims, true);
 }
 
 int dtr_b200_sync(dtr_b200_ctx *c)

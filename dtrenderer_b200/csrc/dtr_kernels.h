@@ -15,6 +15,8 @@ struct SetupParams
 	PrimRecord     *prims;
 	PrimBounds     *bounds;
 	uint32_t       *tileCount; // [numFrames * bandTiles]
+	uint32_t       *coarseCount; // [numFrames * coarseBins * coarseSegs] when two-level binning is on
+	const FrameState *frames;
 	Geometry        g;
 };
 
@@ -26,6 +28,10 @@ struct BinParams
 	const uint32_t   *tileOffset;
 	uint32_t         *lists;
 	uint32_t          listCapacity;
+	// two-level: coarse lists (offsets have one extra trailing entry = total)
+	const uint32_t   *coarseOffset;
+	uint32_t         *coarseLists;
+	uint32_t          coarseCapacity;
 	Geometry          g;
 };
 
@@ -48,8 +54,12 @@ struct RasterParams
 };
 
 void launch_setup(const SetupParams &P, cudaStream_t s);
-void launch_scan(const uint32_t *counts, uint32_t *offsets, uint32_t n, unsigned long long *total,
-                 uint32_t *workCounter, cudaStream_t s);
+// Scans tile counts (-> total[0]) and, when nCoarse > 0, coarse counts (-> total[1]); offsets arrays
+// get one extra trailing entry holding the total.  Also zeroes the raster work counter.
+void launch_scan(const uint32_t *counts, uint32_t *offsets, uint32_t n, const uint32_t *coarseCounts,
+                 uint32_t *coarseOffsets, uint32_t nCoarse, unsigned long long *totals, uint32_t *workCounter,
+                 cudaStream_t s);
+void launch_bin_coarse(const BinParams &P, cudaStream_t s);
 void launch_bin(const BinParams &P, cudaStream_t s);
 void launch_raster(const RasterParams &P, cudaStream_t s);
 

@@ -23,6 +23,12 @@ constexpr int REGION_H    = 16;
 constexpr int SUB_W       = 8;
 constexpr int SUB_H       = 4;
 constexpr int RASTER_THREADS = 256;
+// Two-level binning for frames with many primitives: a coarse bin is 8x8 tiles (512x256 pixels) and
+// a frame's primitive range is cut into segments of COARSE_SEG so that coarse lists are built by
+// (bin, segment) warps in parallel and still come out in submission order.
+constexpr int COARSE_TILES   = 8;
+constexpr int COARSE_SEG     = 4096;
+constexpr int TWO_LEVEL_MIN_PRIMS = 8192; // per frame
 
 enum PrimType : uint32_t
 {
@@ -129,6 +135,8 @@ struct Geometry
 	int32_t bandTileY0, bandTileY1; // tile rows rasterised by this context
 	int32_t bandTiles;          // tilesX * (bandTileY1 - bandTileY0)
 	int32_t numFrames;          // ACTIVE frames of this flush (slots into FrameState[])
+	// two-level binning (0 = off): coarse bins over the band, segments per frame
+	int32_t coarseX, coarseY, coarseBins, coarseSegs;
 };
 
 } // namespace dtr
