@@ -1,0 +1,173 @@
+// DTRRenderB200.h -- host-side mirror of DTRenderer's draw-call API on top of the C ABI.
+//
+// Include this AFTER the reference's own headers (dqn.h, DTRendererRender.h, DTRendererAsset.h):
+// it uses the reference's types as they are (DTRRenderContext, DTRRenderTransform, DTRRenderLight,
+// DTRMesh, DTRBitmap, DqnV2/V3/V4) and provides one function per draw call with the SAME
+// signature, argument meaning and silent-return behaviour (DTRendererRender.h:91-98):
+//
+//     DTRRender_Clear            -> DTRRenderB200_Clear
+//     DTRRender_Triangle         -> DTRRenderB200_Triangle
+//     DTRRender_TexturedTriangle -> DTRRenderB200_TexturedTriangle
+//     DTRRender_Mesh             -> DTRRenderB200_Mesh
+//     DTRRender_Rectangle        -> DTRRenderB200_Rectangle
+//     DTRRender_Bitmap           -> DTRRenderB200_Bitmap
+//     DTRRender_Line             -> DTRRenderB200_Line
+//
+// plus the two frame hooks the app (DTR_Update, DTRenderer.cpp:967-989 / :1097-1102) calls:
+//     DTRRenderB200_BeginFrame(renderBuffer)  after the per-frame z-buffer reset
+//     DTRRenderB200_EndFrame(renderBuffer)    before the platform presents renderBuffer->memory
+//
+// The binding owns one dtr_b200_ctx per DTRRenderBuffer (created on first use) and caches the
+// uploads of DTRMesh / DTRBitmap by address.  No reference source is modified or copied; see
+// INTEGRATION.md for the three-line patch that switches the renderer over.
+#ifndef DTR_RENDER_B200_H
+#define DTR_RENDER_B200_H
+
+#include <map>
+#include <vector>
+
+#include "dtr_b200.h"
+
+struct DTRB200Binding
+{
+	dtr_b200_ctx                  *ctx = nullptr;
+	std::map<const void *, int>    textures; // DTRBitmap::memory -> texId
+	std::map<const DTRMesh *, int> meshes;
+};
+
+inline std::map<const DTRRenderBuffer *, DTRB200Binding> &DTRB200_Bindings()
+{
+	static std::map<const DTRRenderBuffer *, DTRB200Binding> bindings;
+	return bindings;
+}
+
+inline DTRB200Binding *DTRB200_Bind(const DTRRenderBuffer *rb)
+{
+	if (!rb) return nullptr;
+	DTRB200Binding &b = DTRB200_Bindings()[rb];
+	if (!b.ctx && dtr_b200_create(0, rb->width, rb->height, 1, &b.ctx) != DTR_B200_OK) return nullptr;
+	return &b;
+}
+
+inline dtr_b200_transform DTRB200_Transform(const DTRRenderTransform &t)
+{
+	dtr_b200_transform r = {t.rotation, {t.anchor.x, t.anchor.y, t.anchor.z}, {t.scale.x, t.scale.y, t.scale.z}};
+	return r;
+}
+
+inline int DTRB200_Texture(DTRB200Binding *b, const DTRBitmap *bmp)
+{
+	if (!bmp || !bmp->memory) return -1;
+	auto it = b->textures.find(bmp->memory);
+	if (it != b->textures.end()) return it->second;
+	int id = -1;
+	if (dtr_b200_upload_texture(b->ctx, bmp->memory, bmp->dim.w, bmp->dim.h, bmp->bytesPerPixel, &id) != DTR_B200_OK) return -1;
+	b->textures[bmp->memory] = id;
+	return id;
+}
+
+// Frame hooks ------------------------------------------------------------------------------------
+// hostZ == zBuffer freshly reset by the app: only its reset is mirrored (no upload of 8 MB of -FLT_MAX).
+inline void DTRRenderB200_BeginFrame(DTRRenderBuffer *rb)
+{
+	DTRB200Binding *b = DTRB200_Bind(rb);
+	if (b) dtr_b200_begin_frame(b->ctx, 0, nullptr, nullptr);
+}
+
+inline void DTRRenderB200_EndFrame(DTRRenderBuffer *rb)
+{
+	DTRB200Binding *b = DTRB200_Bind(rb);
+	if (b) dtr_b200_end_frame(b->ctx, 0, (uint32_t *)rb->memory, (float *)rb->zBuffer);
+}
+
+// Draw calls -------------------------------------------------------------------------------------
+inline void DTRRenderB200_Clear(DTRRenderContext context, DqnV3 color)
+{
+	DTRB200Binding *b = DTRB200_Bind(context.renderBuffer);
+	if (!b) return;
+	dtr_b200_clear(b->ctx, color.e);
+}
+
+inline void DTRRenderB200_Triangle(DTRRenderContext context, DqnV3 p1, DqnV3 p2, DqnV3 p3, DqnV4 color,
+                                   const DTRRenderTransform transform = DTRRender_DefaultTriangleTransform())
+{
+	DTRB200Binding *b = DTRB200_Bind(context.renderBuffer);
+	if (!b) return;
+	dtr_b200_transform t = DTRB200_Transform(transform);
+	dtr_b200_triangle(b->ctx, p1.e, p2.e, p3.e, color.e, &t);
+}
+
+inline void DTRRenderB200_TexturedTriangle(DTRRenderContext context, DqnV3 p1, DqnV3 p2, DqnV3 p3, DqnV2 uv1, DqnV2 uv2,
+                                           DqnV2 uv3, DTRBitmap *const texture, DqnV4 color,
+                                           const DTRRenderTransform transform = DTRRender_DefaultTriangleTransform())
+{
+	DTRB200Binding *b = DTRB200_Bind(context.renderBuffer);
+	if (!b) return;
+	dtr_b200_transform t = DTRB200_Transform(transform);
+	dtr_b200_textured_triangle(b->ctx, p1.e, p2.e, p3.e, uv1.e, uv2.e, uv3.e, DTRB200_Texture(b, texture), color.e, &t);
+}
+
+inline void DTRRenderB200_Mesh(DTRRenderContext context, PlatformJobQueue *const jobQueue, DTRMesh *const mesh,
+                               DTRRenderLight lighting, const DqnV3 pos, const DTRRenderTransform transform)
+{
+	// same guard as the reference (DTRendererRender.cpp:1402); the job queue itself is not used
+	if (!mesh || !context.renderBuffer || !context.tempStack || !context.api || !jobQueue) return;
+	DTRB200Binding *b = DTRB200_Bind(context.renderBuffer);
+	if (!b) return;
+	int  meshId = -1;
+	auto it     = b->meshes.find(mesh);
+	if (it != b->meshes.end()) meshId = it->second;
+	else
+	{
+		// flatten the per-face index arrays (DTRendererAsset.h:16-26) once
+		std::vector<int32_t> faces((size_t)mesh->numFaces * 9);
+		for (u32 i = 0; i < mesh->numFaces; i++)
+		{
+			const DTRMeshFace &f = mesh->faces[i];
+			if (f.numVertexIndex != 3 || f.numNormalIndex != 3 || f.numTexIndex < 3) return; // reference asserts
+			for (int k = 0; k < 3; k++)
+			{
+				faces[9 * i + k]     = f.vertexIndex[k];
+				faces[9 * i + 3 + k] = f.texIndex[k];
+				faces[9 * i + 6 + k] = f.normalIndex[k];
+			}
+		}
+		dtr_b200_mesh_desc d = {(const float *)mesh->vertexes, mesh->numVertexes, (const float *)mesh->texUV, mesh->numTexUV,
+		                        (const float *)mesh->normals,  mesh->numNormals,  faces.data(),               mesh->numFaces};
+		if (dtr_b200_upload_mesh(b->ctx, &d, DTRB200_Texture(b, &mesh->tex), &meshId) != DTR_B200_OK) return;
+		b->meshes[mesh] = meshId;
+	}
+	dtr_b200_light     l = {(int32_t)lighting.mode, {lighting.vector.x, lighting.vector.y, lighting.vector.z},
+	                        {lighting.color.r, lighting.color.g, lighting.color.b, lighting.color.a}};
+	dtr_b200_transform t = DTRB200_Transform(transform);
+	dtr_b200_mesh(b->ctx, meshId, &l, pos.e, &t);
+}
+
+inline void DTRRenderB200_Rectangle(DTRRenderContext context, DqnV2 min, DqnV2 max, DqnV4 color,
+                                    const DTRRenderTransform transform = DTRRender_DefaultTransform())
+{
+	DTRB200Binding *b = DTRB200_Bind(context.renderBuffer);
+	if (!b) return;
+	dtr_b200_transform t = DTRB200_Transform(transform);
+	dtr_b200_rectangle(b->ctx, min.e, max.e, color.e, &t);
+}
+
+inline void DTRRenderB200_Bitmap(DTRRenderContext context, DTRBitmap *const bitmap, DqnV2 pos,
+                                 const DTRRenderTransform transform = DTRRender_DefaultTransform(),
+                                 DqnV4 color = DqnV4_4f(1, 1, 1, 1))
+{
+	if (!bitmap || !bitmap->memory) return; // DTRendererRender.cpp:1601
+	DTRB200Binding *b = DTRB200_Bind(context.renderBuffer);
+	if (!b) return;
+	dtr_b200_transform t = DTRB200_Transform(transform);
+	dtr_b200_bitmap(b->ctx, DTRB200_Texture(b, bitmap), pos.e, &t, color.e);
+}
+
+inline void DTRRenderB200_Line(DTRRenderContext context, DqnV2i a, DqnV2i b2, DqnV4 color)
+{
+	DTRB200Binding *b = DTRB200_Bind(context.renderBuffer);
+	if (!b) return;
+	dtr_b200_line(b->ctx, a.e, b2.e, color.e);
+}
+
+#endif // DTR_RENDER_B200_H

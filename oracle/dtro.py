@@ -18,6 +18,8 @@ _PATHS = {
     "reference": os.path.join(_HERE, "_ref", "libdtr_ref.so"),
     "reference_markers": os.path.join(_HERE, "_ref", "libdtr_ref_markers.so"),
     "port": os.path.join(_HERE, "libdtr_oracle.so"),
+    # the reference's own types and call signatures driving the CUDA back end (drop-in proof)
+    "reference_api_b200": os.path.join(_HERE, "_ref", "libdtr_ref_b200.so"),
 }
 _LIBS = {}
 
