@@ -66,6 +66,7 @@ SYMBOLS = [
     ("dtr_b200_set_profiling", C.c_int, [C.c_void_p, C.c_int]),
     ("dtr_b200_get_stage_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float * 4), C.POINTER(C.c_int)]),
     ("dtr_b200_reset_stage_ms", C.c_int, [C.c_void_p]),
+    ("dtr_b200_selftest", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     ("dtr_b200_clear", C.c_int, [C.c_void_p, _f]),
     ("dtr_b200_triangle", C.c_int, [C.c_void_p, _f, _f, _f, _f, _T]),
     ("dtr_b200_triangles", C.c_int, [C.c_void_p, C.c_int, _f, _f, _T]),
@@ -240,6 +241,12 @@ class Renderer:
         ms, runs = (C.c_float * 4)(), C.c_int(0)
         self._ck(self.lib.dtr_b200_get_stage_ms(self.ctx, C.byref(ms), C.byref(runs)))
         return dict(setup=ms[0], scan=ms[1], bin=ms[2], raster=ms[3]), runs.value
+
+    def selftest(self):
+        """Mismatches of the device arithmetic self-test (must be 0)."""
+        n = C.c_uint64(1)
+        self._ck(self.lib.dtr_b200_selftest(self.ctx, C.byref(n)))
+        return int(n.value)
 
     def counters(self):
         s = self.stats()

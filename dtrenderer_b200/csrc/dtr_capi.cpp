@@ -723,6 +723,21 @@ int dtr_b200_get_stats(dtr_b200_ctx *c, dtr_b200_stats *out)
 	return DTR_B200_OK;
 }
 
+int dtr_b200_selftest(dtr_b200_ctx *c, uint64_t *mismatches)
+{
+	if (!c || !mismatches) return DTR_B200_ERR_ARG;
+	CU(cudaSetDevice(c->device));
+	unsigned long long *d = nullptr, h = 0;
+	CU(cudaMalloc((void **)&d, sizeof(h)));
+	CU(cudaMemsetAsync(d, 0, sizeof(h), c->stream));
+	launch_selftest_sqrt(d, c->stream);
+	CU(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	CU(cudaFree(d));
+	*mismatches = h;
+	return DTR_B200_OK;
+}
+
 int dtr_b200_set_profiling(dtr_b200_ctx *c, int enable)
 {
 	if (!c) return DTR_B200_ERR_ARG;

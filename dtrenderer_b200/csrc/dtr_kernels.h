@@ -60,6 +60,7 @@ void launch_scan(const uint32_t *counts, uint32_t *offsets, uint32_t n, const ui
                  uint32_t *coarseOffsets, uint32_t nCoarse, unsigned long long *totals, uint32_t *workCounter,
                  cudaStream_t s);
 void launch_bin_coarse(const BinParams &P, cudaStream_t s);
+void launch_selftest_sqrt(unsigned long long *mismatches, cudaStream_t s);
 void launch_bin(const BinParams &P, cudaStream_t s);
 void launch_raster(const RasterParams &P, cudaStream_t s);
 

@@ -150,6 +150,10 @@ int dtr_b200_set_profiling(dtr_b200_ctx *ctx, int enable);
 int dtr_b200_get_stage_ms(dtr_b200_ctx *ctx, float ms[4], int *runs);
 int dtr_b200_reset_stage_ms(dtr_b200_ctx *ctx);
 
+/* Device self-test of the arithmetic shortcuts: the blend's branch-free square root is compared
+ * with IEEE sqrtf on every float in [2^-60, 4).  *mismatches must come back 0. */
+int dtr_b200_selftest(dtr_b200_ctx *ctx, uint64_t *mismatches);
+
 /* ---- draw calls --------------------------------------------------------------------------- */
 int dtr_b200_clear(dtr_b200_ctx *ctx, const float rgb[3]);
 int dtr_b200_triangle(dtr_b200_ctx *ctx, const float p1[3], const float p2[3], const float p3[3],

@@ -260,3 +260,9 @@ def test_null_arguments_are_silent_noops(built):
         r.ctx, 5, (C.c_float * 2)(0, 0), None, None) == -1  # bad texture id is an argument error
     col, z = r.end_frame(0)
     assert np.all(z == Z_RESET)
+
+
+def test_device_arithmetic_selftest(built):
+    """The blend's branch-free sqrt equals IEEE sqrtf on every float in [2^-60, 4)."""
+    r = _renderer(64, 48)
+    assert r.selftest() == 0
