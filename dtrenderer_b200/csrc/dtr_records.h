@@ -14,15 +14,17 @@
 namespace dtr
 {
 
-// Screen tile owned by one CTA of the raster kernel; each of its 8 warps owns a 16x16 region
-// that it walks in 8x4-pixel sub-blocks (one pixel per lane).
+// Screen tile = the unit of binning.  The raster kernel hands 32x32-pixel regions of a tile to
+// single warps; a region is 32 sub-blocks of 8x4 pixels (one sub-block per lane when a triangle is
+// classified against the region, one pixel per lane when a sub-block is rasterised).
 constexpr int TILE_W      = 64;
 constexpr int TILE_H      = 32;
-constexpr int REGION_W    = 16;
-constexpr int REGION_H    = 16;
+constexpr int REGION_W    = 32;
+constexpr int REGION_H    = 32;
 constexpr int SUB_W       = 8;
 constexpr int SUB_H       = 4;
-constexpr int RASTER_THREADS = 256;
+constexpr int RASTER_THREADS = 128;
+constexpr int RASTER_CTAS_PER_SM = 5; // 20 warps per SM, each with 10.4 KB of shared memory
 // Two-level binning for frames with many primitives: a coarse bin is 8x8 tiles (512x256 pixels) and
 // a frame's primitive range is cut into segments of COARSE_SEG so that coarse lists are built by
 // (bin, segment) warps in parallel and still come out in submission order.
@@ -48,14 +50,20 @@ enum PrimFlags : uint32_t
 	PF_TEXTURED     = 1u << 6,
 };
 
-// 40 words.  Word indices of the triangle layout:
+// 40 words = ten 128-bit quads.  Triangle layout: quads 0-3 are the GEOMETRY part (read once per
+// (triangle, region) by one lane), quads 4-9 the SHADING part (copied verbatim into a shared-memory
+// slot that the fragments of the triangle refer to).
 enum TriWord
 {
 	TW_FLAGS = 0, TW_TEX = 1, TW_MIN = 2 /* minx | miny<<16 */, TW_MAX = 3 /* maxx | maxy<<16 */,
-	TW_E0 = 4 /*3*/, TW_DX = 7 /*3*/, TW_DY = 10 /*3*/, TW_INV_AREA = 13, TW_Z1 = 14, TW_DZ2 = 15,
-	TW_DZ3 = 16, TW_COLOR = 17 /*4: linear premultiplied rgba*/, TW_LIGHT = 21 /*9: [vertex][rgb]*/,
-	TW_UV1 = 30 /*2*/, TW_DUV2 = 32 /*2*/, TW_DUV3 = 34 /*2*/,
+	TW_E0 = 4 /*3*/, TW_DX = 7 /*3*/, TW_DY = 10 /*3*/, /* 13..15 unused */
+	TW_INV_AREA = 16, TW_Z1 = 17, TW_DZ2 = 18, TW_DZ3 = 19,
+	TW_COLOR = 20 /*4: linear premultiplied rgba*/, TW_LIGHT = 24 /*9: [vertex][rgb]*/,
+	TW_UV1 = 33 /*2*/, TW_DUV2 = 35 /*2*/, TW_DUV3 = 37 /*2*/,
+	TW_FLAGS_TEX = 39 /* (flags & 0xFF) | texId << 8, repeated for the shading slot */,
 };
+constexpr int TRI_SHADE_QUAD0 = 4; // first quad of the shading part
+constexpr int TRI_SHADE_QUADS = 6;
 // Word indices of the quad layout (rectangle / bitmap / clear / line):
 enum QuadWord
 {
