@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdtr_b200.so")
+# DTR_B200_LIB: developer override used to compare experimental builds of the same C ABI
+LIB_PATH = os.environ.get("DTR_B200_LIB") or os.path.join(_HERE, "libdtr_b200.so")
 
 SHADE_FULLBRIGHT, SHADE_FLAT, SHADE_GOURAUD = 0, 1, 2
 

@@ -20,11 +20,17 @@ namespace dtr
 constexpr int TILE_W      = 64;
 constexpr int TILE_H      = 32;
 constexpr int REGION_W    = 32;
-constexpr int REGION_H    = 32;
+#ifndef DTR_REGION_H
+#define DTR_REGION_H 32
+#endif
+constexpr int REGION_H    = DTR_REGION_H; // 32 or 16
 constexpr int SUB_W       = 8;
 constexpr int SUB_H       = 4;
 constexpr int RASTER_THREADS = 128;
-constexpr int RASTER_CTAS_PER_SM = 5; // 20 warps per SM, each with 10.4 KB of shared memory
+#ifndef DTR_RASTER_CTAS
+#define DTR_RASTER_CTAS 5
+#endif
+constexpr int RASTER_CTAS_PER_SM = DTR_RASTER_CTAS; // 5 x 4 warps per SM, each warp with 10.4 KB of shared memory
 // Two-level binning for frames with many primitives: a coarse bin is 8x8 tiles (512x256 pixels) and
 // a frame's primitive range is cut into segments of COARSE_SEG so that coarse lists are built by
 // (bin, segment) warps in parallel and still come out in submission order.
