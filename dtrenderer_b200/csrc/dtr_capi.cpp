@@ -81,8 +81,8 @@ struct dtr_b200_ctx
 	std::vector<uint8_t>   texIsWhite; // every texel 0xFFFFFFFF: sampling multiplies by exactly 1.0f
 	DevBuf                 dTextures;
 
-	DevBuf dCmd, dPayload, dPrims, dBounds, dTileCount, dTileOffset, dLists, dCoarseOffset, dCoarseLists;
-	unsigned long long *dSetPixels = nullptr; // [0] SetPixel count, [1] list total, [2] coarse list total, [3] work counter
+	DevBuf dCmd, dPayload, dPrims, dBounds, dTileCount, dTileOffset, dOrder, dLists, dCoarseOffset, dCoarseLists;
+	unsigned long long *dSetPixels = nullptr; // [0] SetPixel count, [1] list total, [2] coarse list total, [3] work counter, [4] busy tiles
 	uint64_t            triangles = 0, launches = 0, uploadBytes = 0;
 	bool                     profiling = false;
 	std::vector<cudaEvent_t> events;     // 5 per profiled pipeline
@@ -267,14 +267,19 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 
 	int rc;
 	// tile counts and coarse counts share one buffer so that one memset clears both
-	if ((rc = ensure_dev(c, c->dTileCount, sizeof(uint32_t) * ((size_t)numTiles + numCoarse)))) return rc;
+	// tile counts, coarse counts and the scan's look-back words share one buffer: one memset clears all
+	const size_t countWords  = ((size_t)numTiles + numCoarse + 1) & ~(size_t)1; // keep the 64-bit words aligned
+	const size_t statusWords = scan_status_words(numTiles, numCoarse);
+	if ((rc = ensure_dev(c, c->dTileCount, sizeof(uint32_t) * countWords + sizeof(unsigned long long) * statusWords))) return rc;
+	if ((rc = ensure_dev(c, c->dOrder, sizeof(uint32_t) * std::max<size_t>(numTiles, 1)))) return rc;
 	if ((rc = ensure_dev(c, c->dTileOffset, sizeof(uint32_t) * ((size_t)numTiles + 1)))) return rc;
 	if ((rc = ensure_dev(c, c->dCoarseOffset, sizeof(uint32_t) * ((size_t)numCoarse + 1)))) return rc;
 	if ((rc = ensure_dev(c, c->dPrims, sizeof(PrimRecord) * (size_t)std::max(numPrims, 1u)))) return rc;
 	if ((rc = ensure_dev(c, c->dBounds, sizeof(PrimBounds) * (size_t)std::max(numPrims, 1u)))) return rc;
 	uint32_t *dTileCount = (uint32_t *)c->dTileCount.p, *dCoarseCount = dTileCount + numTiles;
 
-	CU(cudaMemsetAsync(dTileCount, 0, sizeof(uint32_t) * ((size_t)numTiles + numCoarse), c->stream));
+	unsigned long long *dScanStatus = (unsigned long long *)(dTileCount + countWords);
+	CU(cudaMemsetAsync(dTileCount, 0, sizeof(uint32_t) * countWords + sizeof(unsigned long long) * statusWords, c->stream));
 	if ((rc = mark(c))) return rc;
 	if (numPrims)
 	{
@@ -287,13 +292,26 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 		S.tileCount   = dTileCount;
 		S.coarseCount = dCoarseCount;
 		S.frames      = dFrames;
+		S.textures    = (const TexDesc *)c->dTextures.p;
 		S.g           = g;
 		launch_setup(S, c->stream);
 		c->launches++;
 	}
 	if ((rc = mark(c))) return rc;
-	launch_scan(dTileCount, (uint32_t *)c->dTileOffset.p, numTiles, dCoarseCount, (uint32_t *)c->dCoarseOffset.p,
-	            numCoarse, c->dSetPixels + 1, (uint32_t *)(c->dSetPixels + 3), c->stream);
+	ScanParams SC;
+	SC.counts0     = dTileCount;
+	SC.offsets0    = (uint32_t *)c->dTileOffset.p;
+	SC.n0          = numTiles;
+	SC.counts1     = dCoarseCount;
+	SC.offsets1    = (uint32_t *)c->dCoarseOffset.p;
+	SC.n1          = numCoarse;
+	SC.order       = (uint32_t *)c->dOrder.p;
+	SC.status      = dScanStatus;
+	SC.totals      = c->dSetPixels + 1;
+	SC.workCounter = (uint32_t *)(c->dSetPixels + 3);
+	SC.numBusy     = (uint32_t *)(c->dSetPixels + 4);
+	SC.chunks0     = 0;
+	launch_scan(SC, c->stream);
 	c->launches++;
 	if ((rc = mark(c))) return rc;
 
@@ -342,12 +360,14 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	R.bounds     = (const PrimBounds *)c->dBounds.p;
 	R.tileCount  = dTileCount;
 	R.tileOffset = (const uint32_t *)c->dTileOffset.p;
+	R.order      = (const uint32_t *)c->dOrder.p;
 	R.lists      = (const uint32_t *)c->dLists.p;
 	R.textures   = (const TexDesc *)c->dTextures.p;
 	R.setPixels  = c->dSetPixels;
 	R.workCounter    = (uint32_t *)(c->dSetPixels + 3);
-	R.numItems       = 0;
-	R.regionsPerItem = 0;
+	R.numBusy        = (const uint32_t *)(c->dSetPixels + 4);
+	R.numTiles       = 0;
+	R.smallTilesMin  = 0;
 	R.g          = g;
 	launch_raster(R, c->stream);
 	c->launches++;
@@ -481,9 +501,9 @@ int dtr_b200_create(int device, int width, int height, int numFrames, dtr_b200_c
 	if ((e = cudaStreamCreateWithFlags(&n->ownStream, cudaStreamNonBlocking)) != cudaSuccess ||
 	    (e = cudaMalloc((void **)&n->dColor, plane * numFrames * sizeof(uint32_t))) != cudaSuccess ||
 	    (e = cudaMalloc((void **)&n->dDepth, plane * numFrames * sizeof(float))) != cudaSuccess ||
-	    (e = cudaMalloc((void **)&n->dSetPixels, 4 * sizeof(unsigned long long))) != cudaSuccess ||
+	    (e = cudaMalloc((void **)&n->dSetPixels, 8 * sizeof(unsigned long long))) != cudaSuccess ||
 	    (e = cudaMemset(n->dColor, 0, plane * numFrames * sizeof(uint32_t))) != cudaSuccess ||
-	    (e = cudaMemset(n->dSetPixels, 0, 4 * sizeof(unsigned long long))) != cudaSuccess)
+	    (e = cudaMemset(n->dSetPixels, 0, 8 * sizeof(unsigned long long))) != cudaSuccess)
 	{
 		fail(nullptr, DTR_B200_ERR_CUDA, "allocating frame targets", e);
 		dtr_b200_destroy(n);
@@ -510,7 +530,7 @@ void dtr_b200_destroy(dtr_b200_ctx *c)
 		cudaFree(m.faces);
 	}
 	for (auto &t : c->textures) cudaFree((void *)t.texels);
-	DevBuf *bufs[] = {&c->dTextures, &c->dCmd, &c->dPayload, &c->dPrims, &c->dBounds, &c->dTileCount, &c->dTileOffset, &c->dLists,
+	DevBuf *bufs[] = {&c->dTextures, &c->dCmd, &c->dPayload, &c->dPrims, &c->dBounds, &c->dTileCount, &c->dTileOffset, &c->dOrder, &c->dLists,
 	                  &c->dCoarseOffset, &c->dCoarseLists};
 	for (DevBuf *b : bufs) cudaFree(b->p);
 	cudaFree(c->dColor);

@@ -20,16 +20,21 @@ namespace dtr
 constexpr int TILE_W      = 64;
 constexpr int TILE_H      = 32;
 constexpr int REGION_W    = 32;
-#ifndef DTR_REGION_H
-#define DTR_REGION_H 32
-#endif
-constexpr int REGION_H    = DTR_REGION_H; // 32 or 16
+constexpr int REGION_H    = 32;
 constexpr int SUB_W       = 8;
 constexpr int SUB_H       = 4;
 constexpr int RASTER_THREADS = 128;
 #ifndef DTR_RASTER_CTAS
 #define DTR_RASTER_CTAS 5
 #endif
+#ifndef DTR_RASTER_TAIL
+#define DTR_RASTER_TAIL 25
+#endif
+constexpr int RASTER_TAIL_PERCENT = DTR_RASTER_TAIL; // share of the untouched tiles kept for the end of the launch
+#ifndef DTR_RASTER_SMALL
+#define DTR_RASTER_SMALL 10
+#endif
+constexpr int RASTER_SMALL_PERCENT = DTR_RASTER_SMALL; // share of the busy tiles rasterised as four 32x16 items
 constexpr int RASTER_CTAS_PER_SM = DTR_RASTER_CTAS; // 5 x 4 warps per SM, each warp with 10.4 KB of shared memory
 // Two-level binning for frames with many primitives: a coarse bin is 8x8 tiles (512x256 pixels) and
 // a frame's primitive range is cut into segments of COARSE_SEG so that coarse lists are built by
@@ -54,22 +59,24 @@ enum PrimFlags : uint32_t
 	PF_EXACT        = 1u << 4, // integer-valued edge setup: direct evaluation == sequential adds
 	PF_IGNORE_LIGHT = 1u << 5,
 	PF_TEXTURED     = 1u << 6,
+	PF_GREY         = 1u << 7, // linear base colour has r == g == b (so have the three light products)
 };
 
 // 40 words = ten 128-bit quads.  Triangle layout: quads 0-3 are the GEOMETRY part (read once per
-// (triangle, region) by one lane), quads 4-9 the SHADING part (copied verbatim into a shared-memory
+// (triangle, region) by one lane), quads 3-9 the SHADING part (copied verbatim into a shared-memory
 // slot that the fragments of the triangle refer to).
 enum TriWord
 {
 	TW_FLAGS = 0, TW_TEX = 1, TW_MIN = 2 /* minx | miny<<16 */, TW_MAX = 3 /* maxx | maxy<<16 */,
-	TW_E0 = 4 /*3*/, TW_DX = 7 /*3*/, TW_DY = 10 /*3*/, /* 13..15 unused */
+	TW_E0 = 4 /*3*/, TW_DX = 7 /*3*/, TW_DY = 10 /*3*/,
+	TW_TEXELS = 13 /*2: device pointer*/, TW_TEXDIM = 15 /* w | h << 16 */,
 	TW_INV_AREA = 16, TW_Z1 = 17, TW_DZ2 = 18, TW_DZ3 = 19,
 	TW_COLOR = 20 /*4: linear premultiplied rgba*/, TW_LIGHT = 24 /*9: [vertex][rgb]*/,
 	TW_UV1 = 33 /*2*/, TW_DUV2 = 35 /*2*/, TW_DUV3 = 37 /*2*/,
 	TW_FLAGS_TEX = 39 /* (flags & 0xFF) | texId << 8, repeated for the shading slot */,
 };
-constexpr int TRI_SHADE_QUAD0 = 4; // first quad of the shading part
-constexpr int TRI_SHADE_QUADS = 6;
+constexpr int TRI_SHADE_QUAD0 = 3; // first quad of the shading part (quad 3 carries the texture)
+constexpr int TRI_SHADE_QUADS = 7;
 // Word indices of the quad layout (rectangle / bitmap / clear / line):
 enum QuadWord
 {
