@@ -264,6 +264,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	uint32_t numCoarse = numActive * (uint32_t)g.coarseBins * (uint32_t)g.coarseSegs;
 	const FrameState *dFrames = (const FrameState *)c->dCmd.p;
 	const DrawItem   *dItems  = (const DrawItem *)((const uint8_t *)c->dCmd.p + sizeof(FrameState) * numActive);
+	const uint32_t   *dBlockItem = (const uint32_t *)(dItems + numItems);
 
 	int rc;
 	// tile counts and coarse counts share one buffer so that one memset clears both
@@ -285,6 +286,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	{
 		SetupParams S;
 		S.items       = dItems;
+		S.blockItem   = dBlockItem;
 		S.numItems    = (int)numItems;
 		S.numPrims    = numPrims;
 		S.prims       = (PrimRecord *)c->dPrims.p;
@@ -403,7 +405,12 @@ int do_flush(dtr_b200_ctx *c)
 	                 [](const RecItem &a, const RecItem &b) { return a.frame < b.frame; });
 
 	uint32_t numActive = (uint32_t)active.size(), numItems = (uint32_t)c->rec.size();
-	size_t   cmdBytes  = sizeof(FrameState) * numActive + sizeof(DrawItem) * numItems;
+	// command block: FrameState[numActive] | DrawItem[numItems] | item of every setup CTA's first primitive
+	uint64_t totalPrims = 0;
+	for (const RecItem &r : c->rec) totalPrims += r.item.count;
+	if (totalPrims >= (1ull << 31)) return fail(c, DTR_B200_ERR_OVERFLOW, "more than 2^31 primitives in one flush");
+	const size_t numBlocks = (size_t)((totalPrims + SETUP_THREADS - 1) / SETUP_THREADS);
+	size_t   cmdBytes  = sizeof(FrameState) * numActive + sizeof(DrawItem) * numItems + sizeof(uint32_t) * numBlocks;
 	int      rc;
 	if ((rc = ensure_pinned(c, c->staging, c->stagingCap, 0, cmdBytes))) return rc;
 	if ((rc = ensure_dev(c, c->dCmd, cmdBytes))) return rc;
@@ -441,6 +448,16 @@ int do_flush(dtr_b200_ctx *c)
 		if (prim >= (1ull << 31)) return fail(c, DTR_B200_ERR_OVERFLOW, "more than 2^31 primitives in one flush");
 	}
 	if (cur >= 0) fs[cur].primEnd = (uint32_t)prim;
+	{
+		uint32_t *blockItem = (uint32_t *)(it + numItems);
+		uint32_t  cursor    = 0;
+		for (size_t b = 0; b < numBlocks; b++)
+		{
+			const uint64_t first = (uint64_t)b * SETUP_THREADS;
+			while (cursor + 1 < numItems && it[cursor + 1].primBase <= first) cursor++;
+			blockItem[b] = cursor;
+		}
+	}
 	// slots with no items keep primBegin == primEnd
 	for (uint32_t s = 0; s < numActive; s++)
 		if (c->frames[active[s]].recorded == 0) fs[s].primBegin = fs[s].primEnd = 0;

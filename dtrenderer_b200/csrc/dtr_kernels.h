@@ -7,9 +7,12 @@
 namespace dtr
 {
 
+constexpr int SETUP_THREADS = 128;
+
 struct SetupParams
 {
 	const DrawItem *items;
+	const uint32_t *blockItem; // [ceil(numPrims / SETUP_THREADS)] item of each CTA's first primitive
 	int             numItems;
 	uint32_t        numPrims;
 	PrimRecord     *prims;
