@@ -71,9 +71,10 @@ enum TriWord
 	TW_E0 = 4 /*3*/, TW_DX = 7 /*3*/, TW_DY = 10 /*3*/,
 	TW_TEXELS = 13 /*2: device pointer*/, TW_TEXDIM = 15 /* w | h << 16 */,
 	TW_INV_AREA = 16, TW_Z1 = 17, TW_DZ2 = 18, TW_DZ3 = 19,
-	TW_COLOR = 20 /*4: linear premultiplied rgba*/, TW_LIGHT = 24 /*9: [vertex][rgb]*/,
-	TW_UV1 = 33 /*2*/, TW_DUV2 = 35 /*2*/, TW_DUV3 = 37 /*2*/,
-	TW_FLAGS_TEX = 39 /* (flags & 0xFF) | texId << 8, repeated for the shading slot */,
+	TW_COLOR = 20 /*4: linear premultiplied rgba*/,
+	TW_LIGHT_R = 24 /*3: red light product of vertex 1,2,3*/, TW_FLAGS_TEX = 27 /* (flags & 0xFF) | texId << 8 */,
+	TW_LIGHT_G = 28 /*3*/, TW_LIGHT_B = 31 /*3*/,
+	TW_UV1 = 34 /*2*/, TW_DUV2X = 36, TW_DUV2Y = 37, TW_DUV3X = 38, TW_DUV3Y = 39,
 };
 constexpr int TRI_SHADE_QUAD0 = 3; // first quad of the shading part (quad 3 carries the texture)
 constexpr int TRI_SHADE_QUADS = 7;
