@@ -61,6 +61,8 @@ SYMBOLS = [
     ("dtr_b200_sync", C.c_int, [C.c_void_p]),
     ("dtr_b200_end_frame", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     ("dtr_b200_read_frames", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    ("dtr_b200_read_frames_async", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    ("dtr_b200_wait_reads", C.c_int, [C.c_void_p]),
     ("dtr_b200_frame_device_ptrs", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     ("dtr_b200_get_stats", C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     ("dtr_b200_reset_stats", C.c_int, [C.c_void_p]),
@@ -217,6 +219,15 @@ class Renderer:
         """Flush and copy n consecutive frames into caller-owned host memory (raw addresses)."""
         self._ck(self.lib.dtr_b200_read_frames(self.ctx, first, n, C.c_void_p(color_ptr),
                                                C.c_void_p(z_ptr) if z_ptr else None))
+
+    def read_frames_async_ptr(self, first, n, color_ptr, z_ptr=None):
+        """Flush and enqueue the readback of n frames on the copy stream (page-locked host memory);
+        returns at once.  wait_reads() blocks until every outstanding readback has landed."""
+        self._ck(self.lib.dtr_b200_read_frames_async(self.ctx, first, n, C.c_void_p(color_ptr),
+                                                     C.c_void_p(z_ptr) if z_ptr else None))
+
+    def wait_reads(self):
+        self._ck(self.lib.dtr_b200_wait_reads(self.ctx))
 
     def frame_device_ptrs(self, frame=0):
         c, z = C.c_void_p(), C.c_void_p()

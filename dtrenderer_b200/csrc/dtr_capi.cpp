@@ -64,6 +64,11 @@ struct dtr_b200_ctx
 {
 	int          device = 0, width = 0, height = 0, numFrames = 0;
 	cudaStream_t stream = nullptr, ownStream = nullptr;
+	// asynchronous readback (dtr_b200_read_frames_async): a copy stream ordered after the rendering
+	// by renderDone; copyDone lets a later flush that renders into frames still being read wait
+	cudaStream_t copyStream = nullptr;
+	cudaEvent_t  renderDone = nullptr, copyDone = nullptr;
+	int          readLo = 0, readHi = 0; // frames [readLo, readHi) have reads in flight
 	uint32_t    *dColor = nullptr;
 	float       *dDepth = nullptr;
 	Geometry     geom{};
@@ -399,6 +404,13 @@ int do_flush(dtr_b200_ctx *c)
 			active.push_back((uint32_t)f);
 		}
 	if (active.empty()) return 0;
+	if (c->readHi > c->readLo)
+	{
+		// a frame that is still being read back must not be overwritten
+		bool overlap = false;
+		for (uint32_t f : active) overlap = overlap || ((int)f >= c->readLo && (int)f < c->readHi);
+		if (overlap) CU(cudaStreamWaitEvent(c->stream, c->copyDone, 0));
+	}
 
 	// frames are independent, so grouping items by frame (stable) preserves every frame's order
 	std::stable_sort(c->rec.begin(), c->rec.end(),
@@ -516,6 +528,9 @@ int dtr_b200_create(int device, int width, int height, int numFrames, dtr_b200_c
 	size_t plane = (size_t)width * height;
 	cudaError_t e;
 	if ((e = cudaStreamCreateWithFlags(&n->ownStream, cudaStreamNonBlocking)) != cudaSuccess ||
+	    (e = cudaStreamCreateWithFlags(&n->copyStream, cudaStreamNonBlocking)) != cudaSuccess ||
+	    (e = cudaEventCreateWithFlags(&n->renderDone, cudaEventDisableTiming)) != cudaSuccess ||
+	    (e = cudaEventCreateWithFlags(&n->copyDone, cudaEventDisableTiming)) != cudaSuccess ||
 	    (e = cudaMalloc((void **)&n->dColor, plane * numFrames * sizeof(uint32_t))) != cudaSuccess ||
 	    (e = cudaMalloc((void **)&n->dDepth, plane * numFrames * sizeof(float))) != cudaSuccess ||
 	    (e = cudaMalloc((void **)&n->dSetPixels, 8 * sizeof(unsigned long long))) != cudaSuccess ||
@@ -557,6 +572,13 @@ void dtr_b200_destroy(dtr_b200_ctx *c)
 	if (c->staging) cudaFreeHost(c->staging);
 	for (cudaEvent_t e : c->events) cudaEventDestroy(e);
 	for (cudaEvent_t e : c->eventPool) cudaEventDestroy(e);
+	if (c->copyStream)
+	{
+		cudaStreamSynchronize(c->copyStream);
+		cudaStreamDestroy(c->copyStream);
+	}
+	if (c->renderDone) cudaEventDestroy(c->renderDone);
+	if (c->copyDone) cudaEventDestroy(c->copyDone);
 	if (c->ownStream) cudaStreamDestroy(c->ownStream);
 	delete c;
 }
@@ -731,6 +753,44 @@ int dtr_b200_read_frames(dtr_b200_ctx *c, int first, int n, uint32_t *hostColor,
 	if (hostZ)
 		CU(cudaMemcpyAsync(hostZ, c->dDepth + plane * first, plane * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
+	return DTR_B200_OK;
+}
+
+int dtr_b200_read_frames_async(dtr_b200_ctx *c, int first, int n, uint32_t *hostColor, float *hostZ)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (n <= 0 || !valid_frame(c, first) || !valid_frame(c, first + n - 1)) return fail(c, DTR_B200_ERR_ARG, "frame range out of bounds");
+	CU(cudaSetDevice(c->device));
+	int rc = do_flush(c);
+	if (rc) return rc;
+	size_t plane = (size_t)c->width * c->height;
+	CU(cudaEventRecord(c->renderDone, c->stream));
+	CU(cudaStreamWaitEvent(c->copyStream, c->renderDone, 0));
+	if (hostColor)
+		CU(cudaMemcpyAsync(hostColor, c->dColor + plane * first, plane * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copyStream));
+	if (hostZ)
+		CU(cudaMemcpyAsync(hostZ, c->dDepth + plane * first, plane * n * sizeof(float), cudaMemcpyDeviceToHost, c->copyStream));
+	CU(cudaEventRecord(c->copyDone, c->copyStream));
+	// conservative: one range covering every read in flight
+	if (c->readHi > c->readLo)
+	{
+		c->readLo = std::min(c->readLo, first);
+		c->readHi = std::max(c->readHi, first + n);
+	}
+	else
+	{
+		c->readLo = first;
+		c->readHi = first + n;
+	}
+	return DTR_B200_OK;
+}
+
+int dtr_b200_wait_reads(dtr_b200_ctx *c)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->copyStream));
+	c->readLo = c->readHi = 0;
 	return DTR_B200_OK;
 }
 

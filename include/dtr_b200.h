@@ -137,6 +137,14 @@ int dtr_b200_end_frame(dtr_b200_ctx *ctx, int frame, uint32_t *hostColor, float 
 /* Flush, then copy n consecutive frames back in one transfer per plane (either pointer may be
  * NULL): hostColor u32[n*W*H], hostZ f32[n*W*H]; waits for completion. */
 int dtr_b200_read_frames(dtr_b200_ctx *ctx, int firstFrame, int n, uint32_t *hostColor, float *hostZ);
+/* Presentation hand-off without stalling the renderer (the step after the hot path, SURVEY.md §8f
+ * rank 4; the reference presents with StretchDIBits, Win32DTRenderer.cpp:267-284): flush, then
+ * enqueue the same copies on the context's copy stream, ordered after the rendering submitted so
+ * far, and return.  Rendering into OTHER frames may be submitted while the copies are in flight (a
+ * flush that touches a frame still being read waits for the copy on the device).  The host
+ * buffers must be page-locked for the copy to overlap; they are valid after dtr_b200_wait_reads. */
+int dtr_b200_read_frames_async(dtr_b200_ctx *ctx, int firstFrame, int n, uint32_t *hostColor, float *hostZ);
+int dtr_b200_wait_reads(dtr_b200_ctx *ctx);
 /* Device pointers of a frame's planes (u32[W*H], f32[W*H]) for zero-copy consumers
  * (NCCL / peer access / torch views). */
 int dtr_b200_frame_device_ptrs(dtr_b200_ctx *ctx, int frame, void **color, void **z);

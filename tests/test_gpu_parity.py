@@ -266,3 +266,64 @@ def test_device_arithmetic_selftest(built):
     """The blend's branch-free sqrt equals IEEE sqrtf on every float in [2^-60, 4)."""
     r = _renderer(64, 48)
     assert r.selftest() == 0
+
+
+def test_async_readback_double_buffered(built):
+    """read_frames_async + wait_reads returns the same planes as the blocking read, and a flush that
+    renders into a frame whose readback is still in flight waits for the copy (the host buffer keeps
+    the OLD content of that frame)."""
+    import torch
+    w, h, n = 320, 200, 4
+    mesh, tex = scenes.uv_sphere(), scenes.random_texture(32, 32, 3, True)
+    ts = scenes.view_transforms(4096)[7:7 + n]
+    pos = np.zeros((n, 3), np.float32)
+    r = _renderer(w, h, 2 * n)
+
+    def record(first, clear):
+        for f in range(first, first + n):
+            r.begin_frame(f)
+            r.clear(clear)
+        r.mesh_views(mesh, tex, scenes.SHADE_GOURAUD, (1, -1, 1), (1, 1, 1, 1), pos, ts, first)
+
+    host = torch.empty((2, n, h, w), dtype=torch.int32, pin_memory=True)
+    hz = torch.empty((2, n, h, w), dtype=torch.float32, pin_memory=True)
+    record(0, (0.5, 0.0, 1.0))
+    r.read_frames_async_ptr(0, n, host[0].data_ptr(), hz[0].data_ptr())
+    record(n, (0.1, 0.9, 0.2))          # other half: may overlap the copy
+    r.read_frames_async_ptr(n, n, host[1].data_ptr(), hz[1].data_ptr())
+    record(0, (0.0, 0.0, 0.0))          # same frames as the first read: must wait for it on the device
+    r.flush()
+    r.wait_reads()
+    for half, clear in ((0, (0.5, 0.0, 1.0)), (1, (0.1, 0.9, 0.2))):
+        for f in range(n):
+            o = _oracle(w, h)
+            o.clear(clear)
+            o.mesh(mesh, tex, scenes.SHADE_GOURAUD, (1, -1, 1), (1, 1, 1, 1), (0, 0, 0), ts[f])
+            _assert_same(host[half, f].numpy().view(np.uint32), hz[half, f].numpy(), o.color(), o.zbuffer())
+    # and the re-rendered first half is what a blocking read sees now
+    col, z = r.end_frame(0)
+    o = _oracle(w, h)
+    o.clear((0.0, 0.0, 0.0))
+    o.mesh(mesh, tex, scenes.SHADE_GOURAUD, (1, -1, 1), (1, 1, 1, 1), (0, 0, 0), ts[0])
+    _assert_same(col, z, o.color(), o.zbuffer())
+
+
+def test_tiny_translucent_overlaps_keep_submission_order(built):
+    """Thousands of 1-20 pixel triangles, half of them translucent, piled on a small area: fragments
+    of many triangles share one shading batch, and the same pixel occurs several times in a batch.
+    Blending is order dependent, so any reordering inside the fragment queue shows up here."""
+    rng = np.random.default_rng(2024)
+    w, h, n = 96, 80, 6000
+    c = rng.integers(8, [w - 8, h - 8], (n, 1, 2)).astype(np.float32)
+    p = np.concatenate([c + rng.integers(-5, 6, (n, 3, 2)), rng.uniform(0, 255, (n, 3, 1))], 2).astype(np.float32)
+    color = rng.random((n, 4)).astype(np.float32)
+    color[::2, 3] = 1.0
+    o, r = _oracle(w, h), _renderer(w, h)
+    o.reset_counters()
+    r.begin_frame(0)
+    for t in (o, r):
+        t.clear((0.2, 0.4, 0.6))
+        t.triangles(p.reshape(n, 9), color, scenes.DEFAULT_TRIANGLE_TRANSFORM)
+    col, z = r.end_frame(0)
+    _assert_same(col, z, o.color(), o.zbuffer())
+    assert r.stats()["setPixels"] == o.counters()[0]
