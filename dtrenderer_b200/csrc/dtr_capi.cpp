@@ -86,8 +86,8 @@ struct dtr_b200_ctx
 	std::vector<uint8_t>   texIsWhite; // every texel 0xFFFFFFFF: sampling multiplies by exactly 1.0f
 	DevBuf                 dTextures;
 
-	DevBuf dCmd, dPayload, dPrims, dBounds, dTileCount, dTileOffset, dOrder, dLists, dCoarseOffset, dCoarseLists;
-	unsigned long long *dSetPixels = nullptr; // [0] SetPixel count, [1] list total, [2] coarse list total, [3] work counter, [4] busy tiles
+	DevBuf dCmd, dPayload, dPrims, dBounds, dTileCount, dTileOffset, dOrder, dLists, dSegRel;
+	unsigned long long *dSetPixels = nullptr; // [0] SetPixel count, [1] list total, [2] unused, [3] work counter, [4] busy tiles
 	uint64_t            triangles = 0, launches = 0, uploadBytes = 0;
 	bool                     profiling = false;
 	std::vector<cudaEvent_t> events;     // 5 per profiled pipeline
@@ -98,7 +98,7 @@ struct dtr_b200_ctx
 	{
 		bool     valid = false;
 		uint32_t numActive = 0, numItems = 0, numPrims = 0, maxFramePrims = 0;
-		uint64_t listTotal = 0, coarseTotal = 0, triangles = 0;
+		uint64_t listTotal = 0, triangles = 0;
 		Geometry g{};
 	} last;
 
@@ -257,35 +257,31 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 {
 	Geometry g   = c->geom;
 	g.numFrames  = (int32_t)numActive;
-	g.coarseX = g.coarseY = g.coarseBins = g.coarseSegs = 0;
-	if (maxFramePrims >= (uint32_t)TWO_LEVEL_MIN_PRIMS)
-	{
-		g.coarseX    = (g.tilesX + COARSE_TILES - 1) / COARSE_TILES;
-		g.coarseY    = (g.bandTileY1 - g.bandTileY0 + COARSE_TILES - 1) / COARSE_TILES;
-		g.coarseBins = g.coarseX * g.coarseY;
-		g.coarseSegs = (int32_t)((maxFramePrims + COARSE_SEG - 1) / COARSE_SEG);
-	}
-	uint32_t numTiles  = numActive * (uint32_t)g.bandTiles;
-	uint32_t numCoarse = numActive * (uint32_t)g.coarseBins * (uint32_t)g.coarseSegs;
+	g.segs       = (int32_t)std::max<uint32_t>(1u, (maxFramePrims + BIN_SEG - 1) / BIN_SEG);
+	g.pad[0] = g.pad[1] = g.pad[2] = 0;
+	const uint32_t numTiles = numActive * (uint32_t)g.bandTiles;
+	const size_t   numSeg   = (size_t)numTiles * (size_t)g.segs; // (tile, segment) counters
+	if (numSeg >= (1ull << 31)) return fail(c, DTR_B200_ERR_OVERFLOW, "more than 2^31 (tile, segment) counters in one flush");
 	const FrameState *dFrames = (const FrameState *)c->dCmd.p;
 	const DrawItem   *dItems  = (const DrawItem *)((const uint8_t *)c->dCmd.p + sizeof(FrameState) * numActive);
 	const uint32_t   *dBlockItem = (const uint32_t *)(dItems + numItems);
 
 	int rc;
-	// tile counts and coarse counts share one buffer so that one memset clears both
-	// tile counts, coarse counts and the scan's look-back words share one buffer: one memset clears all
-	const size_t countWords  = ((size_t)numTiles + numCoarse + 1) & ~(size_t)1; // keep the 64-bit words aligned
-	const size_t statusWords = scan_status_words(numTiles, numCoarse);
+	// one buffer, one memset: (tile, segment) counts | per-tile counts (segs > 1 only) | look-back words
+	const size_t tileWords   = g.segs > 1 ? (size_t)numTiles : 0;
+	const size_t countWords  = (numSeg + tileWords + 1) & ~(size_t)1; // keep the 64-bit words aligned
+	const size_t statusWords = scan_status_words(numTiles);
 	if ((rc = ensure_dev(c, c->dTileCount, sizeof(uint32_t) * countWords + sizeof(unsigned long long) * statusWords))) return rc;
 	if ((rc = ensure_dev(c, c->dOrder, sizeof(uint32_t) * std::max<size_t>(numTiles, 1)))) return rc;
 	if ((rc = ensure_dev(c, c->dTileOffset, sizeof(uint32_t) * ((size_t)numTiles + 1)))) return rc;
-	if ((rc = ensure_dev(c, c->dCoarseOffset, sizeof(uint32_t) * ((size_t)numCoarse + 1)))) return rc;
+	if ((rc = ensure_dev(c, c->dSegRel, sizeof(uint32_t) * std::max<size_t>(g.segs > 1 ? numSeg : 1, 1)))) return rc;
 	if ((rc = ensure_dev(c, c->dPrims, sizeof(PrimRecord) * (size_t)std::max(numPrims, 1u)))) return rc;
 	if ((rc = ensure_dev(c, c->dBounds, sizeof(PrimBounds) * (size_t)std::max(numPrims, 1u)))) return rc;
-	uint32_t *dTileCount = (uint32_t *)c->dTileCount.p, *dCoarseCount = dTileCount + numTiles;
+	uint32_t *dSegCount  = (uint32_t *)c->dTileCount.p;
+	uint32_t *dTileCount = g.segs > 1 ? dSegCount + numSeg : dSegCount; // with one segment they are the same thing
 
-	unsigned long long *dScanStatus = (unsigned long long *)(dTileCount + countWords);
-	CU(cudaMemsetAsync(dTileCount, 0, sizeof(uint32_t) * countWords + sizeof(unsigned long long) * statusWords, c->stream));
+	unsigned long long *dScanStatus = (unsigned long long *)(dSegCount + countWords);
+	CU(cudaMemsetAsync(dSegCount, 0, sizeof(uint32_t) * countWords + sizeof(unsigned long long) * statusWords, c->stream));
 	if ((rc = mark(c))) return rc;
 	if (numPrims)
 	{
@@ -296,8 +292,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 		S.numPrims    = numPrims;
 		S.prims       = (PrimRecord *)c->dPrims.p;
 		S.bounds      = (PrimBounds *)c->dBounds.p;
-		S.tileCount   = dTileCount;
-		S.coarseCount = dCoarseCount;
+		S.segCount    = dSegCount;
 		S.frames      = dFrames;
 		S.textures    = (const TexDesc *)c->dTextures.p;
 		S.g           = g;
@@ -305,55 +300,53 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 		c->launches++;
 	}
 	if ((rc = mark(c))) return rc;
+	if (g.segs > 1)
+	{
+		TileSumParams TS;
+		TS.segCount  = dSegCount;
+		TS.segRel    = (uint32_t *)c->dSegRel.p;
+		TS.tileCount = dTileCount;
+		TS.numTiles  = numTiles;
+		TS.segs      = (uint32_t)g.segs;
+		launch_tile_sum(TS, c->stream);
+		c->launches++;
+	}
 	ScanParams SC;
-	SC.counts0     = dTileCount;
-	SC.offsets0    = (uint32_t *)c->dTileOffset.p;
-	SC.n0          = numTiles;
-	SC.counts1     = dCoarseCount;
-	SC.offsets1    = (uint32_t *)c->dCoarseOffset.p;
-	SC.n1          = numCoarse;
+	SC.counts      = dTileCount;
+	SC.offsets     = (uint32_t *)c->dTileOffset.p;
+	SC.n           = numTiles;
 	SC.order       = (uint32_t *)c->dOrder.p;
 	SC.status      = dScanStatus;
 	SC.totals      = c->dSetPixels + 1;
 	SC.workCounter = (uint32_t *)(c->dSetPixels + 3);
 	SC.numBusy     = (uint32_t *)(c->dSetPixels + 4);
-	SC.chunks0     = 0;
 	launch_scan(SC, c->stream);
 	c->launches++;
 	if ((rc = mark(c))) return rc;
 
-	uint64_t total = c->last.listTotal, coarseTotal = c->last.coarseTotal;
+	uint64_t total = c->last.listTotal;
 	if (!replay)
 	{
-		unsigned long long t[2] = {0, 0};
-		CU(cudaMemcpyAsync(t, c->dSetPixels + 1, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
+		unsigned long long t = 0;
+		CU(cudaMemcpyAsync(&t, c->dSetPixels + 1, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
 		CU(cudaStreamSynchronize(c->stream));
-		total       = t[0];
-		coarseTotal = numCoarse ? t[1] : 0;
-		if (total >= (1ull << 31) || coarseTotal >= (1ull << 31))
-			return fail(c, DTR_B200_ERR_OVERFLOW, "more than 2^31 (primitive, tile) pairs in one flush");
+		total = t;
+		if (total >= (1ull << 31)) return fail(c, DTR_B200_ERR_OVERFLOW, "more than 2^31 (primitive, tile) pairs in one flush");
 		if ((rc = ensure_dev(c, c->dLists, sizeof(uint32_t) * (size_t)std::max<uint64_t>(total, 1)))) return rc;
-		if ((rc = ensure_dev(c, c->dCoarseLists, sizeof(uint32_t) * (size_t)std::max<uint64_t>(coarseTotal, 1)))) return rc;
 	}
 
 	if (numPrims && total)
 	{
 		BinParams B;
-		B.bounds         = (const PrimBounds *)c->dBounds.p;
-		B.frames         = dFrames;
-		B.tileCount      = dTileCount;
-		B.tileOffset     = (const uint32_t *)c->dTileOffset.p;
-		B.lists          = (uint32_t *)c->dLists.p;
-		B.listCapacity   = (uint32_t)(c->dLists.cap / sizeof(uint32_t));
-		B.coarseOffset   = (const uint32_t *)c->dCoarseOffset.p;
-		B.coarseLists    = (uint32_t *)c->dCoarseLists.p;
-		B.coarseCapacity = (uint32_t)(c->dCoarseLists.cap / sizeof(uint32_t));
-		B.g              = g;
-		if (numCoarse)
-		{
-			launch_bin_coarse(B, c->stream);
-			c->launches++;
-		}
+		B.bounds       = (const PrimBounds *)c->dBounds.p;
+		B.frames       = dFrames;
+		B.segCount     = dSegCount;
+		B.segRel       = (const uint32_t *)c->dSegRel.p;
+		B.tileOffset   = (const uint32_t *)c->dTileOffset.p;
+		B.lists        = (uint32_t *)c->dLists.p;
+		B.listCapacity = (uint32_t)(c->dLists.cap / sizeof(uint32_t));
+		B.groupRows    = 0;
+		B.g            = g;
 		launch_bin(B, c->stream);
 		c->launches++;
 	}
@@ -386,7 +379,6 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	c->last.numItems  = numItems;
 	c->last.numPrims  = numPrims;
 	c->last.listTotal = total;
-	c->last.coarseTotal   = coarseTotal;
 	c->last.maxFramePrims = maxFramePrims;
 	c->last.g         = g;
 	return 0;
@@ -563,7 +555,7 @@ void dtr_b200_destroy(dtr_b200_ctx *c)
 	}
 	for (auto &t : c->textures) cudaFree((void *)t.texels);
 	DevBuf *bufs[] = {&c->dTextures, &c->dCmd, &c->dPayload, &c->dPrims, &c->dBounds, &c->dTileCount, &c->dTileOffset, &c->dOrder, &c->dLists,
-	                  &c->dCoarseOffset, &c->dCoarseLists};
+	                  &c->dSegRel};
 	for (DevBuf *b : bufs) cudaFree(b->p);
 	cudaFree(c->dColor);
 	cudaFree(c->dDepth);

@@ -17,8 +17,7 @@ struct SetupParams
 	uint32_t        numPrims;
 	PrimRecord     *prims;
 	PrimBounds     *bounds;
-	uint32_t       *tileCount; // [numFrames * bandTiles]
-	uint32_t       *coarseCount; // [numFrames * coarseBins * coarseSegs] when two-level binning is on
+	uint32_t       *segCount;  // [numFrames * bandTiles * segs] primitives per (tile, segment); == tile counts when segs == 1
 	const FrameState *frames;
 	const TexDesc  *textures; // texture table: pointer and size are copied into textured records
 	Geometry        g;
@@ -29,37 +28,37 @@ constexpr int SCAN_CHUNK   = SCAN_THREADS * 4; // counts scanned per CTA
 
 struct ScanParams
 {
-	const uint32_t     *counts0;  // per-tile counts [n0]
-	uint32_t           *offsets0; // [n0 + 1]
-	uint32_t            n0;
-	const uint32_t     *counts1;  // coarse counts [n1] (two-level binning), n1 may be 0
-	uint32_t           *offsets1; // [n1 + 1]
-	uint32_t            n1;
-	uint32_t           *order;    // [n0] raster work order: busy tiles first, untouched tiles last
-	unsigned long long *status;   // [chunks0 + chunks1] look-back words, zeroed before the launch
-	unsigned long long *totals;   // [0] list total, [1] coarse list total
+	const uint32_t     *counts;   // per-tile counts [n]
+	uint32_t           *offsets;  // [n + 1]
+	uint32_t            n;
+	uint32_t           *order;    // [n] raster work order: busy tiles first, untouched tiles last
+	unsigned long long *status;   // [chunks] look-back words, zeroed before the launch
+	unsigned long long *totals;   // [0] list total
 	uint32_t           *workCounter;
 	uint32_t           *numBusy;  // number of tiles with primitives
-	uint32_t            chunks0;  // filled by launch_scan
 };
 
-inline uint32_t scan_status_words(uint32_t n0, uint32_t n1)
+inline uint32_t scan_status_words(uint32_t n) { return (n + SCAN_CHUNK - 1) / SCAN_CHUNK + 1; }
+
+// segs > 1 only: per tile, the exclusive prefix of its segment counts and their sum
+struct TileSumParams
 {
-	return (n0 + SCAN_CHUNK - 1) / SCAN_CHUNK + 1 + (n1 + SCAN_CHUNK - 1) / SCAN_CHUNK;
-}
+	const uint32_t *segCount;  // [numTiles * segs]
+	uint32_t       *segRel;    // [numTiles * segs]
+	uint32_t       *tileCount; // [numTiles]
+	uint32_t        numTiles, segs;
+};
 
 struct BinParams
 {
 	const PrimBounds *bounds;
 	const FrameState *frames;
-	const uint32_t   *tileCount;
-	const uint32_t   *tileOffset;
+	const uint32_t   *segCount;   // [numTiles * segs]
+	const uint32_t   *segRel;     // [numTiles * segs] offset of a segment's entries inside its tile list (segs > 1)
+	const uint32_t   *tileOffset; // [numTiles + 1]
 	uint32_t         *lists;
 	uint32_t          listCapacity;
-	// two-level: coarse lists (offsets have one extra trailing entry = total)
-	const uint32_t   *coarseOffset;
-	uint32_t         *coarseLists;
-	uint32_t          coarseCapacity;
+	int32_t           groupRows; // tile rows per CTA, filled by launch_bin
 	Geometry          g;
 };
 
@@ -84,10 +83,10 @@ struct RasterParams
 };
 
 void launch_setup(const SetupParams &P, cudaStream_t s);
-// Scans tile counts (-> total[0]) and, when nCoarse > 0, coarse counts (-> total[1]); offsets arrays
-// get one extra trailing entry holding the total.  Also zeroes the raster work counter.
+// Scans the tile counts (-> totals[0]); the offsets array gets one extra trailing entry holding the
+// total.  Also zeroes the raster work counter and writes the work order.
 void launch_scan(const ScanParams &P, cudaStream_t s);
-void launch_bin_coarse(const BinParams &P, cudaStream_t s);
+void launch_tile_sum(const TileSumParams &P, cudaStream_t s);
 void launch_selftest_sqrt(unsigned long long *mismatches, cudaStream_t s);
 void launch_bin(const BinParams &P, cudaStream_t s);
 void launch_raster(const RasterParams &P, cudaStream_t s);

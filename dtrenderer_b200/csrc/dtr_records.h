@@ -36,12 +36,10 @@ constexpr int RASTER_TAIL_PERCENT = DTR_RASTER_TAIL; // share of the untouched t
 #endif
 constexpr int RASTER_SMALL_PERCENT = DTR_RASTER_SMALL; // share of the busy tiles rasterised as four 32x16 items
 constexpr int RASTER_CTAS_PER_SM = DTR_RASTER_CTAS; // 5 x 4 warps per SM, each warp with 10.4 KB of shared memory
-// Two-level binning for frames with many primitives: a coarse bin is 8x8 tiles (512x256 pixels) and
-// a frame's primitive range is cut into segments of COARSE_SEG so that coarse lists are built by
-// (bin, segment) warps in parallel and still come out in submission order.
-constexpr int COARSE_TILES   = 8;
-constexpr int COARSE_SEG     = 4096;
-constexpr int TWO_LEVEL_MIN_PRIMS = 8192; // per frame
+// Frames with many primitives are binned in segments of BIN_SEG primitives: the setup kernel counts
+// per (tile, segment), so that one CTA per (frame, tile row, segment) can write its part of every
+// tile list independently and the lists still come out in submission order.
+constexpr int BIN_SEG = 8192;
 
 enum PrimType : uint32_t
 {
@@ -157,8 +155,8 @@ struct Geometry
 	int32_t bandTileY0, bandTileY1; // tile rows rasterised by this context
 	int32_t bandTiles;          // tilesX * (bandTileY1 - bandTileY0)
 	int32_t numFrames;          // ACTIVE frames of this flush (slots into FrameState[])
-	// two-level binning (0 = off): coarse bins over the band, segments per frame
-	int32_t coarseX, coarseY, coarseBins, coarseSegs;
+	int32_t segs;               // binning segments per frame (1: a frame's primitives are binned in one go)
+	int32_t pad[3];
 };
 
 } // namespace dtr
