@@ -453,6 +453,10 @@ def run_fill_gpu(args, rank, world, local_rank):
         r.set_band(y0, max(y1, y0 + 1) if y1 > y0 else h)  # (empty bands cannot occur at 4K with N <= 8)
     p, color = scenes.small_triangles(w, h, n, seed=7)  # geometry replicated on every rank
     col_t, dep_t = multigpu.frame_tensors(r, 0)
+    peer = world > 1 and args.gather == "peer"
+    token = torch.zeros(1, device="cuda")
+    if peer:
+        multigpu.share_frames(r, dst=0)  # ranks > 0 now rasterise straight into rank 0's planes
 
     def record():
         r.begin_frame(0)
@@ -473,6 +477,9 @@ def run_fill_gpu(args, rank, world, local_rank):
 
     def step_resident():
         r.replay()
+        if peer:
+            multigpu.band_barrier(token)  # stream-ordered: every band has landed in rank 0's HBM
+            return 0
         if world > 1:
             return multigpu.gather_bands(col_t, dep_t, h, dst=0)
         return 0
@@ -506,7 +513,9 @@ def run_fill_gpu(args, rank, world, local_rank):
     def step_e2e():
         record()
         r.flush()
-        if world > 1:
+        if peer:
+            multigpu.band_barrier(token)
+        elif world > 1:
             multigpu.gather_bands(col_t, dep_t, h, dst=0)
         if rank == 0:
             r.read_frames_ptr(0, 1, host.data_ptr())
@@ -535,8 +544,12 @@ def run_fill_gpu(args, rank, world, local_rank):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "width": w, "height": h, "triangles_per_step": n,
                        "shaded_fragments_per_step": shaded_per_step,
-                       "parallelism": f"sort-first bands x{world}" if world > 1 else "single GPU, whole frame",
+                       "parallelism": (f"sort-first bands x{world}, " + ("bands written into rank 0's HBM over NVLink by the "
+                                       "raster kernel's write-back (CUDA IPC peer memory), stream-ordered barrier"
+                                       if peer else "grouped NCCL send/recv gather")) if world > 1
+                       else "single GPU, whole frame",
                        "nccl_bytes_per_step_into_rank0": nccl_bytes,
+                       "peer_bytes_per_step_into_rank0": (8 * w * (h - multigpu.band_rows(h, world, 0)[1])) if peer else 0,
                        "l2": "one 4K frame (66 MB) + 160 MB of primitive records per step; L2 is not flushed "
                              "between steps (frame planes fit in L2, records do not)"},
             "mtris_per_s": n / (ms_step * 1e-3) / 1e6, "frames_per_s": 1.0 / (ms_step * 1e-3),
@@ -566,6 +579,8 @@ def main():
     ap.add_argument("--views", type=int, default=64, help="viewpoints (frames) per step per GPU")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="fill4k, N>1: how the bands reach rank 0 (peer-memory write-back or NCCL send/recv)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -63,6 +63,10 @@ SYMBOLS = [
     ("dtr_b200_read_frames", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     ("dtr_b200_read_frames_async", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     ("dtr_b200_wait_reads", C.c_int, [C.c_void_p]),
+    ("dtr_b200_export_frames", C.c_int, [C.c_void_p, _u8, _u8]),
+    ("dtr_b200_open_peer_frames", C.c_int, [C.c_void_p, _u8, _u8]),
+    ("dtr_b200_set_output_planes", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("dtr_b200_enable_peer_access", C.c_int, [C.c_void_p, C.c_int]),
     ("dtr_b200_frame_device_ptrs", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     ("dtr_b200_get_stats", C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     ("dtr_b200_reset_stats", C.c_int, [C.c_void_p]),
@@ -228,6 +232,23 @@ class Renderer:
 
     def wait_reads(self):
         self._ck(self.lib.dtr_b200_wait_reads(self.ctx))
+
+    def export_frames(self):
+        """CUDA IPC handles (2 x 64 bytes) of this context's colour and depth planes."""
+        hc, hz = (C.c_uint8 * 64)(), (C.c_uint8 * 64)()
+        self._ck(self.lib.dtr_b200_export_frames(self.ctx, hc, hz))
+        return bytes(hc), bytes(hz)
+
+    def open_peer_frames(self, color_handle, depth_handle):
+        """Render into the frames another process exported (sort-first bands over NVLink)."""
+        hc, hz = (C.c_uint8 * 64)(*color_handle), (C.c_uint8 * 64)(*depth_handle)
+        self._ck(self.lib.dtr_b200_open_peer_frames(self.ctx, hc, hz))
+
+    def set_output_planes(self, color_ptr, depth_ptr):
+        self._ck(self.lib.dtr_b200_set_output_planes(self.ctx, C.c_void_p(color_ptr), C.c_void_p(depth_ptr)))
+
+    def enable_peer_access(self, peer_device):
+        self._ck(self.lib.dtr_b200_enable_peer_access(self.ctx, peer_device))
 
     def frame_device_ptrs(self, frame=0):
         c, z = C.c_void_p(), C.c_void_p()

@@ -69,8 +69,13 @@ struct dtr_b200_ctx
 	cudaStream_t copyStream = nullptr;
 	cudaEvent_t  renderDone = nullptr, copyDone = nullptr;
 	int          readLo = 0, readHi = 0; // frames [readLo, readHi) have reads in flight
-	uint32_t    *dColor = nullptr;
+	uint32_t    *dColor = nullptr; // this context's own frame planes
 	float       *dDepth = nullptr;
+	// where the frames are rendered: the own planes, or planes of a peer GPU (sort-first bands that
+	// write straight into the gathering rank's frames over NVLink, dtr_b200_open_peer_frames)
+	uint32_t    *outColor = nullptr;
+	float       *outDepth = nullptr;
+	void        *ipcColor = nullptr, *ipcDepth = nullptr; // mappings opened from IPC handles
 	Geometry     geom{};
 	int          target = 0;
 
@@ -353,8 +358,8 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	if ((rc = mark(c))) return rc;
 
 	RasterParams R;
-	R.color      = c->dColor;
-	R.depth      = c->dDepth;
+	R.color      = c->outColor;
+	R.depth      = c->outDepth;
 	R.frames     = dFrames;
 	R.prims      = (const PrimRecord *)c->dPrims.p;
 	R.bounds     = (const PrimBounds *)c->dBounds.p;
@@ -534,6 +539,8 @@ int dtr_b200_create(int device, int width, int height, int numFrames, dtr_b200_c
 		return DTR_B200_ERR_CUDA;
 	}
 	n->stream = n->ownStream;
+	n->outColor = n->dColor;
+	n->outDepth = n->dDepth;
 	set_geometry(n, 0, height);
 	// a frame that was never begun starts like the reference's first frame: depth reset
 	for (auto &f : n->frames) f.pendingInit = FI_Z_RESET;
@@ -557,6 +564,8 @@ void dtr_b200_destroy(dtr_b200_ctx *c)
 	DevBuf *bufs[] = {&c->dTextures, &c->dCmd, &c->dPayload, &c->dPrims, &c->dBounds, &c->dTileCount, &c->dTileOffset, &c->dOrder, &c->dLists,
 	                  &c->dSegRel};
 	for (DevBuf *b : bufs) cudaFree(b->p);
+	if (c->ipcColor) cudaIpcCloseMemHandle(c->ipcColor);
+	if (c->ipcDepth) cudaIpcCloseMemHandle(c->ipcDepth);
 	cudaFree(c->dColor);
 	cudaFree(c->dDepth);
 	cudaFree(c->dSetPixels);
@@ -685,10 +694,10 @@ int dtr_b200_begin_frame(dtr_b200_ctx *c, int frame, const uint32_t *hostColor, 
 	size_t     plane = (size_t)c->width * c->height;
 	FrameHost &fh    = c->frames[frame];
 	fh.pendingInit   = 0;
-	if (hostZ) CU(cudaMemcpyAsync(c->dDepth + plane * frame, hostZ, plane * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+	if (hostZ) CU(cudaMemcpyAsync(c->outDepth + plane * frame, hostZ, plane * sizeof(float), cudaMemcpyHostToDevice, c->stream));
 	else fh.pendingInit |= FI_Z_RESET;
 	if (hostColor)
-		CU(cudaMemcpyAsync(c->dColor + plane * frame, hostColor, plane * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+		CU(cudaMemcpyAsync(c->outColor + plane * frame, hostColor, plane * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
 	c->target = frame;
 	return DTR_B200_OK;
 }
@@ -726,8 +735,8 @@ int dtr_b200_end_frame(dtr_b200_ctx *c, int frame, uint32_t *hostColor, float *h
 	if (rc) return rc;
 	size_t plane = (size_t)c->width * c->height;
 	if (hostColor)
-		CU(cudaMemcpyAsync(hostColor, c->dColor + plane * frame, plane * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-	if (hostZ) CU(cudaMemcpyAsync(hostZ, c->dDepth + plane * frame, plane * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaMemcpyAsync(hostColor, c->outColor + plane * frame, plane * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	if (hostZ) CU(cudaMemcpyAsync(hostZ, c->outDepth + plane * frame, plane * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
 	return DTR_B200_OK;
 }
@@ -741,9 +750,9 @@ int dtr_b200_read_frames(dtr_b200_ctx *c, int first, int n, uint32_t *hostColor,
 	if (rc) return rc;
 	size_t plane = (size_t)c->width * c->height;
 	if (hostColor)
-		CU(cudaMemcpyAsync(hostColor, c->dColor + plane * first, plane * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaMemcpyAsync(hostColor, c->outColor + plane * first, plane * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
 	if (hostZ)
-		CU(cudaMemcpyAsync(hostZ, c->dDepth + plane * first, plane * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaMemcpyAsync(hostZ, c->outDepth + plane * first, plane * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
 	return DTR_B200_OK;
 }
@@ -759,9 +768,9 @@ int dtr_b200_read_frames_async(dtr_b200_ctx *c, int first, int n, uint32_t *host
 	CU(cudaEventRecord(c->renderDone, c->stream));
 	CU(cudaStreamWaitEvent(c->copyStream, c->renderDone, 0));
 	if (hostColor)
-		CU(cudaMemcpyAsync(hostColor, c->dColor + plane * first, plane * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copyStream));
+		CU(cudaMemcpyAsync(hostColor, c->outColor + plane * first, plane * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copyStream));
 	if (hostZ)
-		CU(cudaMemcpyAsync(hostZ, c->dDepth + plane * first, plane * n * sizeof(float), cudaMemcpyDeviceToHost, c->copyStream));
+		CU(cudaMemcpyAsync(hostZ, c->outDepth + plane * first, plane * n * sizeof(float), cudaMemcpyDeviceToHost, c->copyStream));
 	CU(cudaEventRecord(c->copyDone, c->copyStream));
 	// conservative: one range covering every read in flight
 	if (c->readHi > c->readLo)
@@ -786,13 +795,71 @@ int dtr_b200_wait_reads(dtr_b200_ctx *c)
 	return DTR_B200_OK;
 }
 
+// ---- rendering into a peer GPU's frames (sort-first bands without a gather step) -----------------
+static_assert(sizeof(cudaIpcMemHandle_t) == DTR_B200_IPC_HANDLE_BYTES, "IPC handle size");
+
+int dtr_b200_export_frames(dtr_b200_ctx *c, uint8_t *colorHandle, uint8_t *depthHandle)
+{
+	if (!c || !colorHandle || !depthHandle) return DTR_B200_ERR_ARG;
+	CU(cudaSetDevice(c->device));
+	cudaIpcMemHandle_t hc, hz;
+	CU(cudaIpcGetMemHandle(&hc, c->dColor));
+	CU(cudaIpcGetMemHandle(&hz, c->dDepth));
+	memcpy(colorHandle, &hc, sizeof(hc));
+	memcpy(depthHandle, &hz, sizeof(hz));
+	return DTR_B200_OK;
+}
+
+int dtr_b200_set_output_planes(dtr_b200_ctx *c, void *color, void *depth)
+{
+	if (!c || ((color == nullptr) != (depth == nullptr))) return DTR_B200_ERR_ARG;
+	CU(cudaSetDevice(c->device));
+	int rc = do_flush(c); // what was recorded so far belongs to the previous target
+	if (rc) return rc;
+	CU(cudaStreamSynchronize(c->stream));
+	c->outColor = color ? (uint32_t *)color : c->dColor;
+	c->outDepth = depth ? (float *)depth : c->dDepth;
+	c->last.valid = false; // a replay must not silently switch targets
+	return DTR_B200_OK;
+}
+
+int dtr_b200_open_peer_frames(dtr_b200_ctx *c, const uint8_t *colorHandle, const uint8_t *depthHandle)
+{
+	if (!c || !colorHandle || !depthHandle) return DTR_B200_ERR_ARG;
+	CU(cudaSetDevice(c->device));
+	if (c->ipcColor || c->ipcDepth) return fail(c, DTR_B200_ERR_ARG, "peer frames already open");
+	cudaIpcMemHandle_t hc, hz;
+	memcpy(&hc, colorHandle, sizeof(hc));
+	memcpy(&hz, depthHandle, sizeof(hz));
+	CU(cudaIpcOpenMemHandle(&c->ipcColor, hc, cudaIpcMemLazyEnablePeerAccess));
+	CU(cudaIpcOpenMemHandle(&c->ipcDepth, hz, cudaIpcMemLazyEnablePeerAccess));
+	return dtr_b200_set_output_planes(c, c->ipcColor, c->ipcDepth);
+}
+
+int dtr_b200_enable_peer_access(dtr_b200_ctx *c, int peerDevice)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	CU(cudaSetDevice(c->device));
+	int can = 0;
+	CU(cudaDeviceCanAccessPeer(&can, c->device, peerDevice));
+	if (!can) return fail(c, DTR_B200_ERR_CUDA, "devices cannot access each other's memory");
+	cudaError_t e = cudaDeviceEnablePeerAccess(peerDevice, 0);
+	if (e == cudaErrorPeerAccessAlreadyEnabled)
+	{
+		cudaGetLastError();
+		return DTR_B200_OK;
+	}
+	CU(e);
+	return DTR_B200_OK;
+}
+
 int dtr_b200_frame_device_ptrs(dtr_b200_ctx *c, int frame, void **color, void **z)
 {
 	if (!c) return DTR_B200_ERR_ARG;
 	if (!valid_frame(c, frame)) return fail(c, DTR_B200_ERR_ARG, "frame out of range");
 	size_t plane = (size_t)c->width * c->height;
-	if (color) *color = c->dColor + plane * frame;
-	if (z) *z = c->dDepth + plane * frame;
+	if (color) *color = c->outColor + plane * frame;
+	if (z) *z = c->outDepth + plane * frame;
 	return DTR_B200_OK;
 }
 

@@ -3,8 +3,14 @@ GPU; torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests) carries
 
 * frame / viewpoint parallel: view i -> rank i mod N; no collective on the data path.
 * sort-first screen bands: rank r rasterises tile-aligned rows [y0, y1) of the SAME frame (every rank
-  runs setup over all primitives but bins and rasterises only its band); one grouped send/recv per
-  frame lands every band directly in rank 0's frame planes (no staging copy, no reduction).
+  runs setup over all primitives but bins and rasterises only its band).  Two ways to assemble the
+  frame on rank 0:
+    - share_frames(): rank 0 exports CUDA IPC handles of its planes once; the other ranks map them
+      and their raster kernels write finished regions straight into rank 0's HBM over NVLink (the
+      transfer is fused into the kernel's write-back, tile by tile; a step ends with a stream-ordered
+      barrier, nothing is copied afterwards);
+    - gather_bands(): one grouped NCCL send/recv per frame lands every band in rank 0's planes (the
+      baseline the peer-write path is measured against; also what the gloo CPU tests exercise).
 """
 import numpy as np
 
@@ -69,3 +75,26 @@ def gather_bands(color, depth, height, dst=0, group=None):
         for req in dist.batch_isend_irecv(ops):
             req.wait()
     return int(sum(int(np.prod(o.tensor.shape)) * o.tensor.element_size() for o in ops))
+
+
+def share_frames(renderer, dst=0, group=None):
+    """Sort-first bands over peer memory: rank `dst` exports its frame planes, every other rank maps
+    them and renders into them from now on.  Collective (one 128-byte broadcast)."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == dst:
+        hc, hz = renderer.export_frames()
+        buf.copy_(torch.tensor(list(hc + hz), dtype=torch.uint8))
+    dist.broadcast(buf, src=dst, group=group)
+    if rank != dst:
+        raw = bytes(buf.cpu().tolist())
+        renderer.open_peer_frames(raw[:64], raw[64:])
+
+
+def band_barrier(token, group=None):
+    """Stream-ordered barrier after a band-split step: when it completes on rank 0 every rank's
+    raster kernel (enqueued before it on the same stream) has finished writing its band."""
+    import torch.distributed as dist
+    dist.all_reduce(token, group=group)

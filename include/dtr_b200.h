@@ -145,6 +145,21 @@ int dtr_b200_read_frames(dtr_b200_ctx *ctx, int firstFrame, int n, uint32_t *hos
  * buffers must be page-locked for the copy to overlap; they are valid after dtr_b200_wait_reads. */
 int dtr_b200_read_frames_async(dtr_b200_ctx *ctx, int firstFrame, int n, uint32_t *hostColor, float *hostZ);
 int dtr_b200_wait_reads(dtr_b200_ctx *ctx);
+/* Sort-first screen bands WITHOUT a gather step: every rank rasterises its band
+ * (dtr_b200_set_band) but writes the finished regions straight into the gathering rank's frame
+ * planes over NVLink, from inside the raster kernel's write-back -- the transfer overlaps the
+ * rasterisation tile by tile and nothing is copied afterwards.  The planes have the layout of
+ * DTRRenderBuffer (DTRendererRender.h:14-25), F frames back to back.
+ *   dtr_b200_export_frames        rank 0: CUDA IPC handles of its colour / depth planes
+ *   dtr_b200_open_peer_frames     other ranks (other processes): map them and render into them
+ *   dtr_b200_set_output_planes    same-process variant: raw pointers of another context's planes
+ *                                 (after dtr_b200_enable_peer_access); NULL, NULL = own planes again
+ * The caller orders "all ranks finished" before reading the frames (a barrier / stream event). */
+#define DTR_B200_IPC_HANDLE_BYTES 64
+int dtr_b200_export_frames(dtr_b200_ctx *ctx, uint8_t *colorHandle, uint8_t *depthHandle);
+int dtr_b200_open_peer_frames(dtr_b200_ctx *ctx, const uint8_t *colorHandle, const uint8_t *depthHandle);
+int dtr_b200_set_output_planes(dtr_b200_ctx *ctx, void *color, void *depth);
+int dtr_b200_enable_peer_access(dtr_b200_ctx *ctx, int peerDevice);
 /* Device pointers of a frame's planes (u32[W*H], f32[W*H]) for zero-copy consumers
  * (NCCL / peer access / torch views). */
 int dtr_b200_frame_device_ptrs(dtr_b200_ctx *ctx, int frame, void **color, void **z);

@@ -327,3 +327,29 @@ def test_tiny_translucent_overlaps_keep_submission_order(built):
     col, z = r.end_frame(0)
     _assert_same(col, z, o.color(), o.zbuffer())
     assert r.stats()["setPixels"] == o.counters()[0]
+
+
+def test_band_split_peer_write_two_gpus(built):
+    """Sort-first bands over peer memory: the second GPU's raster kernel writes its band straight into
+    the first GPU's frame planes; the assembled frame equals the single-GPU frame.  (Needs 2 GPUs.)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    w, h = 1024, 768
+    scene = scenes.fill_scene(w, h, 20000, seed=11) + scenes.cfg1_scene(w, h)[1:]
+    _, full_c, full_z = _render_gpu(w, h, scene)
+    from dtrenderer_b200 import api
+    r0, r1 = api.Renderer(w, h, 1, 0), api.Renderer(w, h, 1, 1)
+    r1.enable_peer_access(0)
+    c0, z0 = r0.frame_device_ptrs(0)
+    r1.set_output_planes(c0, z0)
+    r0.set_band(0, 352)
+    r1.set_band(352, h)
+    for r in (r0, r1):
+        r.begin_frame(0)
+        scenes.replay(scene, r)
+        r.flush()
+    r1.sync()
+    col, z = r0.end_frame(0)
+    assert np.array_equal(col, full_c) and np.array_equal(z.view(np.uint32), full_z.view(np.uint32))
+    assert r0.stats()["setPixels"] + r1.stats()["setPixels"] == _render_gpu(w, h, scene)[0].stats()["setPixels"]
