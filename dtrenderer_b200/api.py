@@ -83,6 +83,7 @@ SYMBOLS = [
     ("dtr_b200_rectangle", C.c_int, [C.c_void_p, _f, _f, _f, _T]),
     ("dtr_b200_bitmap", C.c_int, [C.c_void_p, C.c_int, _f, _T, _f]),
     ("dtr_b200_line", C.c_int, [C.c_void_p, _i32, _i32, _f]),
+    ("dtr_b200_set_debug_markers", C.c_int, [C.c_void_p, C.c_int]),
 ]
 
 _lib = None
@@ -232,6 +233,10 @@ class Renderer:
 
     def wait_reads(self):
         self._ck(self.lib.dtr_b200_wait_reads(self.ctx))
+
+    def set_debug_markers(self, enable=True):
+        """Emit the overlay of the reference's default (DTR_DEBUG_RENDER 1) build from rectangle/bitmap."""
+        self._ck(self.lib.dtr_b200_set_debug_markers(self.ctx, 1 if enable else 0))
 
     def export_frames(self):
         """CUDA IPC handles (2 x 64 bytes) of this context's colour and depth planes."""

@@ -69,6 +69,7 @@ struct dtr_b200_ctx
 	cudaStream_t copyStream = nullptr;
 	cudaEvent_t  renderDone = nullptr, copyDone = nullptr;
 	int          readLo = 0, readHi = 0; // frames [readLo, readHi) have reads in flight
+	bool         debugMarkers = false;  // emit the reference's DTR_DEBUG_RENDER overlay (dtr_b200_set_debug_markers)
 	uint32_t    *dColor = nullptr; // this context's own frame planes
 	float       *dDepth = nullptr;
 	// where the frames are rendered: the own planes, or planes of a peer GPU (sort-first bands that
@@ -1035,39 +1036,11 @@ int dtr_b200_mesh(dtr_b200_ctx *c, int meshId, const dtr_b200_light *light, cons
 	return dtr_b200_mesh_views(c, meshId, light, 1, pos, t, c->target);
 }
 
-int dtr_b200_rectangle(dtr_b200_ctx *c, const float mn[2], const float mx[2], const float color[4],
-                       const dtr_b200_transform *t)
+namespace
 {
-	if (!c) return DTR_B200_ERR_ARG;
-	if (!mn || !mx || !color) return DTR_B200_OK;
-	if (!t) t = &kDefaultTransform;
-	PrimRecord r;
-	if (!setup_quad(c->width, c->height, mn, mx, t->rotation, t->anchor, t->scale, color, false, -1, 0, 0, &r))
-		return DTR_B200_OK;
-	return record_raw(c, r);
-}
-
-int dtr_b200_bitmap(dtr_b200_ctx *c, int texId, const float pos[2], const dtr_b200_transform *t, const float color[4])
+// DTRRender_Line (:294-356) as one PRIM_LINE record
+int emit_line(dtr_b200_ctx *c, const int32_t a[2], const int32_t b[2], const float color[4])
 {
-	if (!c) return DTR_B200_ERR_ARG;
-	if (!pos) return DTR_B200_OK;
-	if (texId < 0 || texId >= (int)c->textures.size()) return fail(c, DTR_B200_ERR_ARG, "texId out of range");
-	if (!t) t = &kDefaultTransform;
-	const float white[4] = {1, 1, 1, 1};
-	if (!color) color = white;
-	const TexDesc &td    = c->textures[texId];
-	float          mn[2] = {pos[0], pos[1]};
-	float          mx[2] = {pos[0] + (float)td.w, pos[1] + (float)td.h}; // min + dim (:1607-1608)
-	PrimRecord     r;
-	if (!setup_quad(c->width, c->height, mn, mx, t->rotation, t->anchor, t->scale, color, true, texId, td.w, td.h, &r))
-		return DTR_B200_OK;
-	return record_raw(c, r);
-}
-
-int dtr_b200_line(dtr_b200_ctx *c, const int32_t a[2], const int32_t b[2], const float color[4])
-{
-	if (!c) return DTR_B200_ERR_ARG;
-	if (!a || !b || !color) return DTR_B200_OK;
 	// DTRRender_Line (:294-356): x-major integer DDA after the optional axis swap
 	int ax = a[0], ay = a[1], bx = b[0], by = b[1];
 	int steep = std::abs(ax - bx) < std::abs(ay - by);
@@ -1098,6 +1071,103 @@ int dtr_b200_line(dtr_b200_ctx *c, const int32_t a[2], const int32_t b[2], const
 	r.w[QW_LINE + 4] = (uint32_t)delta;
 	r.w[QW_LINE + 5] = (uint32_t)steep;
 	return record_raw(c, r);
+}
+
+int emit_line4(dtr_b200_ctx *c, int x0, int y0, int x1, int y1, const float color[4])
+{
+	const int32_t a[2] = {x0, y0}, b[2] = {x1, y1};
+	return emit_line(c, a, b, color);
+}
+
+int emit_rectangle(dtr_b200_ctx *c, const float mn[2], const float mx[2], const float color[4], const dtr_b200_transform *t);
+
+// The four bounding-box lines the reference's debug build draws (:492-501, :732-741); the corners
+// are truncated to integers like DqnV2i_2f does.
+int emit_bbox_lines(dtr_b200_ctx *c, const float bounds[4], const float color[4])
+{
+	const int x0 = (int)bounds[0], y0 = (int)bounds[1], x1 = (int)bounds[2], y1 = (int)bounds[3];
+	int rc;
+	if ((rc = emit_line4(c, x0, y0, x0, y1, color))) return rc;
+	if ((rc = emit_line4(c, x0, y1, x1, y1, color))) return rc;
+	if ((rc = emit_line4(c, x1, y1, x1, y0, color))) return rc;
+	return emit_line4(c, x1, y0, x0, y0, color);
+}
+
+// DTRRender_Rectangle (:415-513) including, when enabled, its DTR_DEBUG_RENDER block: bounding-box
+// lines in the rectangle's colour AFTER the linear/premultiply conversion (the reference reuses the
+// converted variable, and DTRRender_Line converts it again), and a green outline when rotation > 0.
+int emit_rectangle(dtr_b200_ctx *c, const float mn[2], const float mx[2], const float color[4], const dtr_b200_transform *t)
+{
+	PrimRecord r;
+	float      pts[4][2], bounds[4];
+	int        rc = 0;
+	if (setup_quad(c->width, c->height, mn, mx, t->rotation, t->anchor, t->scale, color, false, -1, 0, 0, &r, pts, bounds))
+		rc = record_raw(c, r);
+	if (rc || !c->debugMarkers) return rc;
+	float lin[4];
+	to_linear_premul(color, lin);
+	if ((rc = emit_bbox_lines(c, bounds, lin))) return rc;
+	if (t->rotation > 0)
+	{
+		const float green[4] = {0, 1, 0, 1};
+		for (int i = 0; i < 4 && !rc; i++)
+			rc = emit_line4(c, (int)pts[i][0], (int)pts[i][1], (int)pts[(i + 1) & 3][0], (int)pts[(i + 1) & 3][1], green);
+	}
+	return rc;
+}
+} // namespace
+
+int dtr_b200_line(dtr_b200_ctx *c, const int32_t a[2], const int32_t b[2], const float color[4])
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (!a || !b || !color) return DTR_B200_OK;
+	return emit_line(c, a, b, color);
+}
+
+int dtr_b200_set_debug_markers(dtr_b200_ctx *c, int enable)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	c->debugMarkers = enable != 0;
+	return DTR_B200_OK;
+}
+
+int dtr_b200_rectangle(dtr_b200_ctx *c, const float mn[2], const float mx[2], const float color[4],
+                       const dtr_b200_transform *t)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (!mn || !mx || !color) return DTR_B200_OK;
+	if (!t) t = &kDefaultTransform;
+	return emit_rectangle(c, mn, mx, color, t);
+}
+int dtr_b200_bitmap(dtr_b200_ctx *c, int texId, const float pos[2], const dtr_b200_transform *t, const float color[4])
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (!pos) return DTR_B200_OK;
+	if (texId < 0 || texId >= (int)c->textures.size()) return fail(c, DTR_B200_ERR_ARG, "texId out of range");
+	if (!t) t = &kDefaultTransform;
+	const float white[4] = {1, 1, 1, 1};
+	if (!color) color = white;
+	const TexDesc &td    = c->textures[texId];
+	float          mn[2] = {pos[0], pos[1]};
+	float          mx[2] = {pos[0] + (float)td.w, pos[1] + (float)td.h}; // min + dim (:1607-1608)
+	PrimRecord     r;
+	float          pts[4][2], bounds[4];
+	int            rc = 0;
+	if (setup_quad(c->width, c->height, mn, mx, t->rotation, t->anchor, t->scale, color, true, texId, td.w, td.h, &r, pts, bounds))
+		rc = record_raw(c, r);
+	if (rc || !c->debugMarkers) return rc;
+	// DebugRenderMarkers(pList, 4, transform, bbox, basis, vertex markers) (:719-771, :1783-1790):
+	// red bounding box; the basis is only drawn for 3-point lists; a 10x10 rectangle per corner in
+	// green, blue, purple, red -- each of which draws its own debug bounding box in turn
+	const float red[4] = {1, 0, 0, 1};
+	if ((rc = emit_bbox_lines(c, bounds, red))) return rc;
+	const float markerColor[4][4] = {{0, 1, 0, 1}, {0, 0, 1, 1}, {1, 0, 1, 1}, {1, 0, 0, 1}};
+	for (int i = 0; i < 4 && !rc; i++)
+	{
+		const float a[2] = {pts[i][0] - 5.0f, pts[i][1] - 5.0f}, b[2] = {pts[i][0] + 5.0f, pts[i][1] + 5.0f};
+		rc = emit_rectangle(c, a, b, markerColor[i], &kDefaultTransform);
+	}
+	return rc;
 }
 
 } // extern "C"

@@ -187,9 +187,13 @@ inline void to_linear_premul(const float c[4], float out[4])
 inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // Rectangle (texW == 0) or bitmap quad -> PrimRecord.  Returns false when nothing can be drawn.
+// outPoints (optional): the four transformed corners, Basis/XAxis/Point/YAxis order;
+// outBounds (optional): their unclipped bounding box {minx, miny, maxx, maxy} -- both are filled
+// even when the quad itself is invisible (the reference's debug overlay still draws then).
 inline bool setup_quad(int W, int H, const float mn[2], const float mx[2], float rotation,
                        const float anchor[2], const float scale[2], const float color[4], bool bitmap,
-                       int texId, int texW, int texH, PrimRecord *rec)
+                       int texId, int texW, int texH, PrimRecord *rec, float (*outPoints)[2] = nullptr,
+                       float *outBounds = nullptr)
 {
 	std::memset(rec, 0, sizeof(*rec));
 	// TransformRectPoints (:378-393)
@@ -208,6 +212,16 @@ inline bool setup_quad(int W, int H, const float mn[2], const float mx[2], float
 	{
 		bminx = ref_minf(bminx, p[i][0]); bminy = ref_minf(bminy, p[i][1]);
 		bmaxx = ref_maxf(bmaxx, p[i][0]); bmaxy = ref_maxf(bmaxy, p[i][1]);
+	}
+	if (outPoints)
+		for (int i = 0; i < 4; i++)
+		{
+			outPoints[i][0] = p[i][0];
+			outPoints[i][1] = p[i][1];
+		}
+	if (outBounds)
+	{
+		outBounds[0] = bminx; outBounds[1] = bminy; outBounds[2] = bmaxx; outBounds[3] = bmaxy;
 	}
 	// clip to (0,0)-(W,H) (:436-440,1628-1632; dqn.h:3071-3081)
 	float cmaxx = ref_minf(bmaxx, (float)W - 0.0f), cmaxy = ref_minf(bmaxy, (float)H - 0.0f);

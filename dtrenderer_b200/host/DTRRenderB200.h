@@ -28,6 +28,10 @@
 
 #include "dtr_b200.h"
 
+#ifndef DTR_B200_DEBUG_MARKERS
+#define DTR_B200_DEBUG_MARKERS 0
+#endif
+
 struct DTRB200Binding
 {
 	dtr_b200_ctx                  *ctx = nullptr;
@@ -45,7 +49,13 @@ inline DTRB200Binding *DTRB200_Bind(const DTRRenderBuffer *rb)
 {
 	if (!rb) return nullptr;
 	DTRB200Binding &b = DTRB200_Bindings()[rb];
-	if (!b.ctx && dtr_b200_create(0, rb->width, rb->height, 1, &b.ctx) != DTR_B200_OK) return nullptr;
+	if (!b.ctx)
+	{
+		if (dtr_b200_create(0, rb->width, rb->height, 1, &b.ctx) != DTR_B200_OK) return nullptr;
+		// DTR_B200_DEBUG_MARKERS 1 reproduces the overlay of the reference's default
+		// (DTR_DEBUG_RENDER 1) build: bounding boxes, rotated outlines, bitmap corner markers
+		dtr_b200_set_debug_markers(b.ctx, DTR_B200_DEBUG_MARKERS);
+	}
 	return &b;
 }
 

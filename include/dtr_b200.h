@@ -199,6 +199,12 @@ int dtr_b200_rectangle(dtr_b200_ctx *ctx, const float min[2], const float max[2]
 int dtr_b200_bitmap(dtr_b200_ctx *ctx, int texId, const float pos[2],
                     const dtr_b200_transform *transform, const float color[4]);
 int dtr_b200_line(dtr_b200_ctx *ctx, const int32_t a[2], const int32_t b[2], const float color[4]);
+/* DTR_DEBUG_RENDER parity: when enabled, dtr_b200_rectangle and
+ * dtr_b200_bitmap also emit the overlay of the reference's DEFAULT build -- bounding-box lines,
+ * the green outline of rotated rectangles, and for bitmaps the red bounding box plus a 10x10
+ * rectangle per corner (DTRendererRender.cpp:492-512, 719-771, 1783-1790).  Off by default
+ * (== the reference compiled with DTR_DEBUG_RENDER 0). */
+int dtr_b200_set_debug_markers(dtr_b200_ctx *ctx, int enable);
 
 #ifdef __cplusplus
 }

@@ -353,3 +353,40 @@ def test_band_split_peer_write_two_gpus(built):
     col, z = r0.end_frame(0)
     assert np.array_equal(col, full_c) and np.array_equal(z.view(np.uint32), full_z.view(np.uint32))
     assert r0.stats()["setPixels"] + r1.stats()["setPixels"] == _render_gpu(w, h, scene)[0].stats()["setPixels"]
+
+
+def test_debug_marker_overlay_matches_reference_default_build(built):
+    """with dtr_b200_set_debug_markers the rectangle / bitmap calls also draw the
+    DTR_DEBUG_RENDER overlay, and the frame equals the reference's DEFAULT build (markers on)."""
+    from oracle import dtro
+    if not dtro.available("reference_markers"):
+        pytest.skip("oracle/_ref/libdtr_ref_markers.so not built")
+    rng = np.random.default_rng(5)
+    w, h = 640, 400
+    texs = [scenes.random_texture(24, 17, 2, False), scenes.random_texture(40, 40, 3, True)]
+    o = dtro.Oracle(w, h, "reference_markers")
+    r = _renderer(w, h)
+    r.set_debug_markers(True)
+    r.begin_frame(0)
+    o.reset_counters()
+    for t in (o, r):
+        t.clear((0.5, 0.0, 1.0))
+    scene = scenes.cfg1_scene(w, h)[1:]
+    scenes.replay(scene, o)
+    scenes.replay(scene, r)
+    for i in range(24):
+        tr = scenes.transform7(float(rng.uniform(-2, 3)) if i % 3 else 0.0, (*rng.random(2), 0.0),
+                               (float(rng.uniform(0.5, 3)), float(rng.uniform(0.5, 3)), 1.0))
+        col = (*rng.random(3).tolist(), float(rng.choice([1.0, rng.random()])))
+        if i % 2:
+            mn = rng.uniform(-30, [w, h]).astype(np.float32)
+            mx = mn + rng.uniform(1, 150, 2).astype(np.float32)
+            for t in (o, r):
+                t.rectangle(mn, mx, col, tr)
+        else:
+            pos = rng.uniform(-20, [w, h]).astype(np.float32)
+            for t in (o, r):
+                t.bitmap(texs[(i // 2) % 2], pos, tr, col)
+    col, z = r.end_frame(0)
+    _assert_same(col, z, o.color(), o.zbuffer())
+    assert r.stats()["setPixels"] == o.counters()[0]
