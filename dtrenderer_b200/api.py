@@ -84,6 +84,8 @@ SYMBOLS = [
     ("dtr_b200_bitmap", C.c_int, [C.c_void_p, C.c_int, _f, _T, _f]),
     ("dtr_b200_line", C.c_int, [C.c_void_p, _i32, _i32, _f]),
     ("dtr_b200_set_debug_markers", C.c_int, [C.c_void_p, C.c_int]),
+    ("dtr_b200_upload_font", C.c_int, [C.c_void_p, _u8, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    ("dtr_b200_text", C.c_int, [C.c_void_p, C.c_int, _f, C.c_char_p, _f, C.c_int]),
 ]
 
 _lib = None
@@ -142,6 +144,7 @@ class Renderer:
         self.ctx = h
         self._tex = {}    # id(array) -> (texId, array)
         self._mesh = {}   # (id(mesh dict), texId) -> meshId
+        self._font = {}   # id(atlas) -> (fontId, font)
 
     # ---- plumbing ----------------------------------------------------------------------------
     def _ck(self, rc):
@@ -233,6 +236,28 @@ class Renderer:
 
     def wait_reads(self):
         self._ck(self.lib.dtr_b200_wait_reads(self.ctx))
+
+    def upload_font(self, font):
+        """font = (atlas u8[h, w], packedchars (scenes.PACKEDCHAR), cpMin, cpMax) -- a flattened DTRFont."""
+        key = id(font[0])
+        if key in self._font:
+            return self._font[key][0]
+        atlas, chars, cp_min, cp_max = font
+        a = np.ascontiguousarray(atlas, dtype=np.uint8)
+        ch = np.ascontiguousarray(chars)
+        if ch.dtype.itemsize != 28 or ch.size != cp_max - cp_min:
+            raise ValueError("packedchars must be 28-byte stbtt_packedchar records, one per codepoint")
+        fid = C.c_int(-1)
+        self._ck(self.lib.dtr_b200_upload_font(self.ctx, a.ctypes.data_as(_u8), a.shape[1], a.shape[0],
+                                               ch.ctypes.data_as(C.c_void_p), cp_min, cp_max, C.byref(fid)))
+        self._font[key] = (fid.value, font)
+        return fid.value
+
+    def text(self, font, pos, text, color, length=-1):
+        """DTRRender_Text (DTRendererRender.h:91)."""
+        fid = self.upload_font(font)
+        raw = text.encode("latin-1") if isinstance(text, str) else text
+        self._ck(self.lib.dtr_b200_text(self.ctx, fid, _fp(_fa(pos, 2)), raw, _fp(_fa(color, 4)), length))
 
     def set_debug_markers(self, enable=True):
         """Emit the overlay of the reference's default (DTR_DEBUG_RENDER 1) build from rectangle/bitmap."""

@@ -11,6 +11,7 @@
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <string>
@@ -69,6 +70,13 @@ struct dtr_b200_ctx
 	cudaStream_t copyStream = nullptr;
 	cudaEvent_t  renderDone = nullptr, copyDone = nullptr;
 	int          readLo = 0, readHi = 0; // frames [readLo, readHi) have reads in flight
+	struct FontHost
+	{
+		uint8_t                         *dAtlas = nullptr;
+		int                              w = 0, h = 0, cpMin = 0, cpMax = 0;
+		std::vector<dtr_b200_packedchar> chars;
+	};
+	std::vector<FontHost> fonts;
 	bool         debugMarkers = false;  // emit the reference's DTR_DEBUG_RENDER overlay (dtr_b200_set_debug_markers)
 	uint32_t    *dColor = nullptr; // this context's own frame planes
 	float       *dDepth = nullptr;
@@ -562,6 +570,7 @@ void dtr_b200_destroy(dtr_b200_ctx *c)
 		cudaFree(m.faces);
 	}
 	for (auto &t : c->textures) cudaFree((void *)t.texels);
+	for (auto &f : c->fonts) cudaFree(f.dAtlas);
 	DevBuf *bufs[] = {&c->dTextures, &c->dCmd, &c->dPayload, &c->dPrims, &c->dBounds, &c->dTileCount, &c->dTileOffset, &c->dOrder, &c->dLists,
 	                  &c->dSegRel};
 	for (DevBuf *b : bufs) cudaFree(b->p);
@@ -1122,6 +1131,80 @@ int dtr_b200_line(dtr_b200_ctx *c, const int32_t a[2], const int32_t b[2], const
 	if (!c) return DTR_B200_ERR_ARG;
 	if (!a || !b || !color) return DTR_B200_OK;
 	return emit_line(c, a, b, color);
+}
+
+int dtr_b200_upload_font(dtr_b200_ctx *c, const uint8_t *atlas, int atlasWidth, int atlasHeight,
+                         const dtr_b200_packedchar *chars, int codepointMin, int codepointMax, int *fontId)
+{
+	if (!c || !fontId) return DTR_B200_ERR_ARG;
+	if (!atlas || !chars || atlasWidth <= 0 || atlasHeight <= 0 || codepointMax <= codepointMin)
+		return fail(c, DTR_B200_ERR_ARG, "bad font");
+	CU(cudaSetDevice(c->device));
+	dtr_b200_ctx::FontHost f;
+	f.w = atlasWidth; f.h = atlasHeight; f.cpMin = codepointMin; f.cpMax = codepointMax;
+	f.chars.assign(chars, chars + (codepointMax - codepointMin));
+	const size_t bytes = (size_t)atlasWidth * atlasHeight;
+	CU(cudaMalloc((void **)&f.dAtlas, bytes));
+	CU(cudaMemcpy(f.dAtlas, atlas, bytes, cudaMemcpyHostToDevice));
+	c->fonts.push_back(std::move(f));
+	*fontId = (int)c->fonts.size() - 1;
+	return DTR_B200_OK;
+}
+
+int dtr_b200_text(dtr_b200_ctx *c, int fontId, const float pos[2], const char *text, const float color[4], int len)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (!text || !pos || !color) return DTR_B200_OK; // the reference returns silently (:197-200)
+	if (fontId < 0 || fontId >= (int)c->fonts.size()) return fail(c, DTR_B200_ERR_ARG, "fontId out of range");
+	const dtr_b200_ctx::FontHost &f = c->fonts[fontId];
+	if (len == -1) len = (int)strlen(text);
+	float col[4];
+	to_linear_premul(color, col);
+	float       posx = pos[0], posy = pos[1];
+	const float ipw = 1.0f / (float)f.w, iph = 1.0f / (float)f.h; // stbtt_GetPackedQuad (stb_truetype.h:3739-3763)
+	for (int index = 0; index < len; index++)
+	{
+		const int charIndex = (int)text[index] - f.cpMin;
+		if (charIndex < 0 || charIndex >= f.cpMax - f.cpMin) return fail(c, DTR_B200_ERR_ARG, "character outside the font's codepoint range");
+		const dtr_b200_packedchar &b = f.chars[charIndex];
+		const float qx0 = (float)(int)std::floor((double)((posx + b.xoff) + 0.5f));
+		const float qy0 = (float)(int)std::floor((double)((posy + b.yoff) + 0.5f));
+		const float s0 = (float)b.x0 * ipw, t0 = (float)b.y0 * iph, s1 = (float)b.x1 * ipw, t1 = (float)b.y1 * iph;
+		posx += b.xadvance;
+		const float    fminx = s0 * (float)f.w, fminy = t1 * (float)f.h; // fontRect.min (:226-227)
+		const float    fmaxx = s1 * (float)f.w, fmaxy = t0 * (float)f.h; // fontRect.max
+		const uint32_t pitch = (uint32_t)f.w;
+		const uint32_t fontOffset = (uint32_t)(fminx + (fmaxy * (float)pitch)); // (:236)
+		const float    fho = b.yoff2 + b.yoff;                                   // (:246)
+		const int      fw = std::abs((int)(fminx - fmaxx)), fh = std::abs((int)(fminy - fmaxy));
+		if (fw <= 0 || fh <= 0) continue;
+		// pixels touched: actualX / actualY are monotone in x / y (:264-265)
+		int x0 = (int)(qx0 + 0.0f), x1 = (int)(qx0 + (float)(fw - 1)) + 1;
+		int y0 = (int)((qy0 + 0.0f) - fho), y1 = (int)((qy0 + (float)(fh - 1)) - fho) + 1;
+		x0 = clampi(x0, 0, c->width); x1 = clampi(x1, 0, c->width);
+		y0 = clampi(y0, 0, c->height); y1 = clampi(y1, 0, c->height);
+		if (x1 <= x0 || y1 <= y0) continue;
+		PrimRecord r;
+		memset(&r, 0, sizeof(r));
+		r.w[QW_FLAGS] = PRIM_GLYPH;
+		r.w[QW_MIN]   = (uint32_t)x0 | ((uint32_t)y0 << 16);
+		r.w[QW_MAX]   = (uint32_t)x1 | ((uint32_t)y1 << 16);
+		for (int i = 0; i < 4; i++) r.w[QW_COLOR + i] = f2u(col[i]);
+		const unsigned long long ap = (unsigned long long)(uintptr_t)f.dAtlas;
+		r.w[QW_GLYPH + 0] = (uint32_t)ap;
+		r.w[QW_GLYPH + 1] = (uint32_t)(ap >> 32);
+		r.w[QW_GLYPH + 2] = fontOffset;
+		r.w[QW_GLYPH + 3] = pitch;
+		r.w[QW_GLYPH + 4] = (uint32_t)fw;
+		r.w[QW_GLYPH + 5] = (uint32_t)fh;
+		r.w[QW_GLYPH + 6] = f2u(qx0);
+		r.w[QW_GLYPH + 7] = f2u(qy0);
+		r.w[QW_GLYPH + 8] = f2u(fho);
+		r.w[QW_GLYPH + 9] = (uint32_t)((size_t)f.w * f.h);
+		int rc = record_raw(c, r);
+		if (rc) return rc;
+	}
+	return DTR_B200_OK;
 }
 
 int dtr_b200_set_debug_markers(dtr_b200_ctx *c, int enable)

@@ -49,6 +49,7 @@ enum PrimType : uint32_t
 	PRIM_BITMAP    = 3, // bilinear bitmap blit (:1596-1791)
 	PRIM_CLEAR     = 4, // colour-only clear (:1793-1815)
 	PRIM_LINE      = 5, // integer DDA line (:294-356)
+	PRIM_GLYPH     = 6, // one character of DTRRender_Text: 1-byte-per-pixel atlas x colour (:193-273)
 };
 
 enum PrimFlags : uint32_t
@@ -83,6 +84,8 @@ enum QuadWord
 	QW_P = 4 /*8: Basis, XAxis, Point, YAxis (x,y)*/, QW_COLOR = 12 /*4*/, QW_INVX = 16, QW_INVY = 17,
 	QW_TEXDIM = 18 /* w | h<<16 */, QW_PACKED = 19 /* PRIM_CLEAR: packed 0x00RRGGBB */,
 	QW_LINE = 20 /*6: ax, ay, run, dist, delta, steep */,
+	QW_GLYPH = 20 /*10: atlas lo, atlas hi, fontOffset, pitch, fontWidth, fontHeight, screen x (f32), screen y (f32),
+	                    fontHeightOffset (f32), atlas size in bytes */,
 };
 
 struct alignas(16) PrimRecord

@@ -12,6 +12,7 @@
 //     DTRRender_Rectangle        -> DTRRenderB200_Rectangle
 //     DTRRender_Bitmap           -> DTRRenderB200_Bitmap
 //     DTRRender_Line             -> DTRRenderB200_Line
+//     DTRRender_Text             -> DTRRenderB200_Text
 //
 // plus the two frame hooks the app (DTR_Update, DTRenderer.cpp:967-989 / :1097-1102) calls:
 //     DTRRenderB200_BeginFrame(renderBuffer)  after the per-frame z-buffer reset
@@ -37,6 +38,7 @@ struct DTRB200Binding
 	dtr_b200_ctx                  *ctx = nullptr;
 	std::map<const void *, int>    textures; // DTRBitmap::memory -> texId
 	std::map<const DTRMesh *, int> meshes;
+	std::map<const void *, int>    fonts; // DTRFont::bitmap -> fontId
 };
 
 inline std::map<const DTRRenderBuffer *, DTRB200Binding> &DTRB200_Bindings()
@@ -171,6 +173,27 @@ inline void DTRRenderB200_Bitmap(DTRRenderContext context, DTRBitmap *const bitm
 	if (!b) return;
 	dtr_b200_transform t = DTRB200_Transform(transform);
 	dtr_b200_bitmap(b->ctx, DTRB200_Texture(b, bitmap), pos.e, &t, color.e);
+}
+
+// DTRFont::atlas is an array of stbtt_packedchar, which dtr_b200_packedchar mirrors field for field.
+inline void DTRRenderB200_Text(DTRRenderContext context, const DTRFont font, DqnV2 pos, const char *const text,
+                               DqnV4 color = DqnV4_4f(1, 1, 1, 1), i32 len = -1)
+{
+	if (!text || !font.bitmap || !font.atlas) return; // DTRendererRender.cpp:197-200
+	static_assert(sizeof(dtr_b200_packedchar) == sizeof(stbtt_packedchar), "packed char layout");
+	DTRB200Binding *b = DTRB200_Bind(context.renderBuffer);
+	if (!b) return;
+	int  id = -1;
+	auto it = b->fonts.find(font.bitmap);
+	if (it != b->fonts.end()) id = it->second;
+	else
+	{
+		if (dtr_b200_upload_font(b->ctx, font.bitmap, font.bitmapDim.w, font.bitmapDim.h, (const dtr_b200_packedchar *)font.atlas,
+		                         font.codepointRange.min, font.codepointRange.max, &id) != DTR_B200_OK)
+			return;
+		b->fonts[font.bitmap] = id;
+	}
+	dtr_b200_text(b->ctx, id, pos.e, text, color.e, len);
 }
 
 inline void DTRRenderB200_Line(DTRRenderContext context, DqnV2i a, DqnV2i b2, DqnV4 color)

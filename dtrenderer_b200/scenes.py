@@ -149,6 +149,49 @@ def cfg1_scene(width=800, height=600, seed=3):
     return cmds
 
 
+# stbtt_packedchar (external/stb_truetype.h:522-527): what DTRFont::atlas holds per codepoint
+PACKEDCHAR = np.dtype([("x0", "<u2"), ("y0", "<u2"), ("x1", "<u2"), ("y1", "<u2"), ("xoff", "<f4"), ("yoff", "<f4"),
+                       ("xadvance", "<f4"), ("xoff2", "<f4"), ("yoff2", "<f4")])
+
+
+def synthetic_font(seed=1, cp_min=32, cp_max=127, cell=(12, 16), cols=16):
+    """A DTRFont-shaped font without a .ttf: (atlas u8[h, w], packedchars[cp_max - cp_min], cp_min,
+    cp_max).  Every codepoint gets a random-size glyph of random 8-bit coverage (a third of the
+    texels 0) in its own atlas cell, and stb_truetype-style metrics: fractional offsets and advance,
+    yoff negative (stb's y axis points down).  One spare row below every glyph keeps the reference's
+    off-by-one row read (DTRendererRender.cpp:253) inside the atlas."""
+    rng = np.random.default_rng(seed)
+    n = cp_max - cp_min
+    rows = (n + cols - 1) // cols
+    cw, ch = cell
+    atlas = np.zeros((rows * ch + 2, cols * cw), np.uint8)
+    chars = np.zeros(n, PACKEDCHAR)
+    for i in range(n):
+        gx, gy = (i % cols) * cw + 1, (i // cols) * ch + 1
+        w, h = int(rng.integers(2, cw - 2)), int(rng.integers(3, ch - 3))
+        cov = rng.integers(0, 256, (h + 1, w), np.uint8)
+        cov[rng.random((h + 1, w)) < 0.33] = 0
+        atlas[gy:gy + h + 1, gx:gx + w] = cov
+        xoff, yoff = float(rng.uniform(-1.0, 2.0)), float(rng.uniform(-(h + 2.0), -1.0))
+        chars[i] = (gx, gy, gx + w, gy + h, xoff, yoff, float(rng.uniform(w, w + 3.0)), xoff + w, yoff + h)
+    return atlas, chars, cp_min, cp_max
+
+
+def text_scene(width, height, seed=4):
+    """DTRRender_Text over a cleared frame and a translucent rectangle: strings in several colours,
+    partly translucent, some running off the right / bottom / top edges."""
+    rng = np.random.default_rng(seed)
+    font = synthetic_font(seed)
+    scene = [("clear", dict(rgb=(0.1, 0.2, 0.3))),
+             ("rectangle", dict(mn=(width * 0.2, height * 0.2), mx=(width * 0.8, height * 0.7), color=(0.9, 0.8, 0.1, 0.6)))]
+    words = ["DTRenderer", "B200 back end", "shaded Gpixels/s: 62.2", "The quick brown fox_jumps|over {lazy} dogs 0123456789"]
+    for i in range(14):
+        pos = (float(rng.uniform(-20, width - 30)), float(rng.uniform(-4, height + 6)))
+        color = (*rng.random(3).tolist(), float(rng.choice([1.0, rng.random()])))
+        scene.append(("text", dict(font=font, pos=pos, text=words[i % len(words)], color=color)))
+    return scene
+
+
 def replay(scene, target):
     """Issue the scene's draw calls, in order, on ``target``."""
     for name, kw in scene:

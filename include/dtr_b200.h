@@ -199,6 +199,22 @@ int dtr_b200_rectangle(dtr_b200_ctx *ctx, const float min[2], const float max[2]
 int dtr_b200_bitmap(dtr_b200_ctx *ctx, int texId, const float pos[2],
                     const dtr_b200_transform *transform, const float color[4]);
 int dtr_b200_line(dtr_b200_ctx *ctx, const int32_t a[2], const int32_t b[2], const float color[4]);
+/* DTRRender_Text (DTRendererRender.h:91, DTRendererRender.cpp:193-273).
+ * A font is the reference's DTRFont flattened (DTRendererAsset.h:44-52): the 1-byte-per-pixel atlas
+ * and one packed-char entry per codepoint of [codepointMin, codepointMax) -- dtr_b200_packedchar
+ * has the layout of stbtt_packedchar (external/stb_truetype.h:522-527), i.e. DTRFont::atlas can be
+ * passed as is.  dtr_b200_text lays the string out on the host exactly like the reference
+ * (stbtt_GetPackedQuad with align_to_integer) and records one glyph primitive per character;
+ * len == -1 means strlen(text).  Characters outside the font's range are an argument error (the
+ * reference asserts). */
+typedef struct dtr_b200_packedchar
+{
+	uint16_t x0, y0, x1, y1; /* glyph box in the atlas */
+	float    xoff, yoff, xadvance, xoff2, yoff2;
+} dtr_b200_packedchar;
+int dtr_b200_upload_font(dtr_b200_ctx *ctx, const uint8_t *atlas, int atlasWidth, int atlasHeight,
+                         const dtr_b200_packedchar *chars, int codepointMin, int codepointMax, int *fontId);
+int dtr_b200_text(dtr_b200_ctx *ctx, int fontId, const float pos[2], const char *text, const float color[4], int len);
 /* DTR_DEBUG_RENDER parity: when enabled, dtr_b200_rectangle and
  * dtr_b200_bitmap also emit the overlay of the reference's DEFAULT build -- bounding-box lines,
  * the green outline of rotated rectangles, and for bitmaps the red bounding box plus a 10x10

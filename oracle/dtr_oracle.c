@@ -711,3 +711,44 @@ void dtro_line(dtro_ctx *c, const int32_t a_in[2], const int32_t b_in[2], const 
 		if (acc > run) { ny += delta; acc -= (run * 2); }
 	}
 }
+
+void dtro_text(dtro_ctx *c, const uint8_t *atlas, int atlasW, int atlasH, const dtro_packedchar *chars,
+               int cpMin, int cpMax, const float pos_in[2], const char *text, const float color[4], int len)
+{
+	/* DTRRender_Text (:193-273) with stbtt_GetPackedQuad(..., align_to_integer = true)
+	 * (external/stb_truetype.h:3739-3763) restated inline.  Quirks kept: the range check at :212-216
+	 * can never fire; glyph rows are read from fontHeight down to 1 (:253), not fontHeight-1..0. */
+	(void)cpMax;
+	if (!text || !atlas || !chars) return;
+	if (len == -1) len = (int)strlen(text);
+	rgba  col = to_linear_premul(color);
+	float posx = pos_in[0], posy = pos_in[1];
+	const float ipw = 1.0f / (float)atlasW, iph = 1.0f / (float)atlasH;
+	for (int index = 0; index < len; index++)
+	{
+		const dtro_packedchar *b = chars + ((int)text[index] - cpMin);
+		const float qx0 = (float)(int)floor((posx + b->xoff) + 0.5f);
+		const float qy0 = (float)(int)floor((posy + b->yoff) + 0.5f);
+		const float s0 = (float)b->x0 * ipw, t0 = (float)b->y0 * iph, s1 = (float)b->x1 * ipw, t1 = (float)b->y1 * iph;
+		posx += b->xadvance;
+		const float fminx = s0 * (float)atlasW, fminy = t1 * (float)atlasH; /* fontRect.min */
+		const float fmaxx = s1 * (float)atlasW, fmaxy = t0 * (float)atlasH; /* fontRect.max */
+		const uint32_t pitch  = (uint32_t)atlasW;
+		const uint32_t offset = (uint32_t)(fminx + (fmaxy * (float)pitch));
+		const uint8_t *fontPtr = atlas + offset;
+		const float    fho = b->yoff2 + b->yoff;
+		const int fontWidth = abs((int)(fminx - fmaxx)), fontHeight = abs((int)(fminy - fmaxy));
+		for (int y = 0; y < fontHeight; y++)
+			for (int x = 0; x < fontWidth; x++)
+			{
+				const int     yOffset = fontHeight - y;
+				const uint8_t srcA    = fontPtr[x + (yOffset * (int)pitch)];
+				if (srcA == 0) continue;
+				const float srcANorm = (float)srcA / 255.0f;
+				rgba r = {col.r * srcANorm, col.g * srcANorm, col.b * srcANorm, col.a * srcANorm};
+				const int actualX = (int)(qx0 + (float)x);
+				const int actualY = (int)((qy0 + (float)y) - fho);
+				blend_pixel(c, actualX, actualY, r);
+			}
+	}
+}

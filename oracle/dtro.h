@@ -60,6 +60,17 @@ void dtro_bitmap(dtro_ctx *c, const uint8_t *tex, int texW, int texH, const floa
                  const float transform[7], const float color[4]);
 void dtro_line(dtro_ctx *c, const int32_t a[2], const int32_t b[2], const float color[4]);
 
+/* DTRRender_Text (DTRendererRender.cpp:193-273).  The font is passed flattened: the 1-byte-per-pixel
+ * atlas (DTRFont::bitmap, bitmapDim) and one dtro_packedchar per codepoint of [cpMin, cpMax) -- the
+ * layout of stbtt_packedchar (external/stb_truetype.h:522-527), which is what DTRFont::atlas holds. */
+typedef struct dtro_packedchar
+{
+	uint16_t x0, y0, x1, y1;
+	float    xoff, yoff, xadvance, xoff2, yoff2;
+} dtro_packedchar;
+void dtro_text(dtro_ctx *c, const uint8_t *atlas, int atlasW, int atlasH, const dtro_packedchar *chars,
+               int cpMin, int cpMax, const float pos[2], const char *text, const float color[4], int len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,11 @@ _LIBS = {}
 
 SHADE_FULLBRIGHT, SHADE_FLAT, SHADE_GOURAUD = 0, 1, 2
 
+# stbtt_packedchar (external/stb_truetype.h:522-527) == dtro_packedchar == dtr_b200_packedchar
+PACKEDCHAR = np.dtype([("x0", "<u2"), ("y0", "<u2"), ("x1", "<u2"), ("y1", "<u2"), ("xoff", "<f4"), ("yoff", "<f4"),
+                       ("xadvance", "<f4"), ("xoff2", "<f4"), ("yoff2", "<f4")])
+assert PACKEDCHAR.itemsize == 28
+
 _f = C.POINTER(C.c_float)
 _u8 = C.POINTER(C.c_uint8)
 _i32 = C.POINTER(C.c_int32)
@@ -58,6 +63,8 @@ def _load(kind):
                               _u8, C.c_int, C.c_int, C.c_int, _f, _f, _f, _f]
     lib.dtro_rectangle.argtypes = [C.c_void_p, _f, _f, _f, _f]
     lib.dtro_bitmap.argtypes = [C.c_void_p, _u8, C.c_int, C.c_int, _f, _f, _f]
+    if hasattr(lib, "dtro_text"):
+        lib.dtro_text.argtypes = [C.c_void_p, _u8, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, _f, C.c_char_p, _f, C.c_int]
     lib.dtro_line.argtypes = [C.c_void_p, _i32, _i32, _f]
     _LIBS[kind] = lib
     return lib
@@ -163,6 +170,15 @@ class Oracle:
         h, w = tex.shape[:2]
         self.lib.dtro_bitmap(self.ctx, tex.ctypes.data_as(_u8), w, h, _fp(_fa(pos, 2)),
                              _fp(_fa(transform, 7)), _fp(_fa(color, 4)))
+
+    def text(self, font, pos, text, color, length=-1):
+        """font = (atlas u8[h, w], packedchars structured array PACKEDCHAR, cpMin, cpMax)."""
+        atlas, chars, cp_min, cp_max = font
+        atlas = np.ascontiguousarray(atlas, dtype=np.uint8)
+        chars = np.ascontiguousarray(chars, dtype=PACKEDCHAR)
+        self.lib.dtro_text(self.ctx, atlas.ctypes.data_as(C.POINTER(C.c_uint8)), atlas.shape[1], atlas.shape[0],
+                           chars.ctypes.data_as(C.c_void_p), cp_min, cp_max, _fp(_fa(pos, 2)),
+                           text.encode("latin-1") if isinstance(text, str) else text, _fp(_fa(color, 4)), length)
 
     def line(self, a, b, color):
         a = np.ascontiguousarray(a, dtype=np.int32)

@@ -226,4 +226,16 @@ void dtro_line(dtro_ctx *c, const int32_t a[2], const int32_t b[2], const float 
 	DTRRenderB200_Line(c->ctx, DqnV2i_2i(a[0], a[1]), DqnV2i_2i(b[0], b[1]), DqnV4_4f(color[0], color[1], color[2], color[3]));
 }
 
+void dtro_text(dtro_ctx *c, const uint8_t *atlas, int atlasW, int atlasH, const dtro_packedchar *chars,
+               int cpMin, int cpMax, const float pos[2], const char *text, const float color[4], int len)
+{
+	Begin(c);
+	DTRFont font        = {};
+	font.bitmap         = (u8 *)atlas;
+	font.bitmapDim      = DqnV2i_2i(atlasW, atlasH);
+	font.codepointRange = DqnV2i_2i(cpMin, cpMax);
+	font.atlas          = (stbtt_packedchar *)chars;
+	DTRRenderB200_Text(c->ctx, font, DqnV2_2f(pos[0], pos[1]), text, DqnV4_4f(color[0], color[1], color[2], color[3]), len);
+}
+
 } // extern "C"

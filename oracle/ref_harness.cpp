@@ -212,4 +212,17 @@ void dtro_line(dtro_ctx *c, const int32_t a[2], const int32_t b[2], const float 
 	               DqnV4_4f(color[0], color[1], color[2], color[3]));
 }
 
+void dtro_text(dtro_ctx *c, const uint8_t *atlas, int atlasW, int atlasH, const dtro_packedchar *chars,
+               int cpMin, int cpMax, const float pos[2], const char *text, const float color[4], int len)
+{
+	static_assert(sizeof(dtro_packedchar) == sizeof(stbtt_packedchar), "dtro_packedchar mirrors stbtt_packedchar");
+	DTRFont font        = {};
+	font.bitmap         = (u8 *)atlas;
+	font.bitmapDim      = DqnV2i_2i(atlasW, atlasH);
+	font.codepointRange = DqnV2i_2i(cpMin, cpMax);
+	font.sizeInPt       = 0;
+	font.atlas          = (stbtt_packedchar *)chars;
+	DTRRender_Text(c->ctx, font, DqnV2_2f(pos[0], pos[1]), text, DqnV4_4f(color[0], color[1], color[2], color[3]), len);
+}
+
 } // extern "C"

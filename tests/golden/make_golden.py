@@ -91,12 +91,13 @@ SCENES = {
     "odd_333x217": (333, 217, lambda: scenes.cfg1_scene(333, 217) + scenes.mesh_scene(333, 217, textured=True, tex_size=32)[1:]),
     "edges_320x200": (320, 200, lambda: edge_scene(320, 200)),
     "lines_256x192": (256, 192, lambda: line_scene(256, 192)),
+    "text_320x200": (320, 200, lambda: scenes.text_scene(320, 200)),
     "view_37_of_4096_640x360": (640, 360, lambda: [("clear", dict(rgb=(0.5, 0, 1)))] + [
         ("mesh", dict(mesh=scenes.uv_sphere(), tex=scenes.random_texture(128, 128, 1, True),
                       light_mode=scenes.SHADE_GOURAUD, light_vector=(1, -1, 1), light_color=(1, 1, 1, 1),
                       pos=(0.1, -0.05, 0.0), transform=scenes.view_transforms(4096)[37]))]),
 }
-SMALL = ["edges_320x200", "lines_256x192", "odd_333x217"]
+SMALL = ["edges_320x200", "lines_256x192", "odd_333x217", "text_320x200"]
 
 
 def digest(a):

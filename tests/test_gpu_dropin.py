@@ -11,7 +11,7 @@ from golden_scenes import DIGESTS, SCENES, digest
 
 pytestmark = pytest.mark.gpu
 
-NAMES = ["cfg1_800x600", "edges_320x200", "lines_256x192", "odd_333x217", "flat_640x480",
+NAMES = ["cfg1_800x600", "edges_320x200", "lines_256x192", "text_320x200", "odd_333x217", "flat_640x480",
          "cfg3_textured_overlays_720p", "view_37_of_4096_640x360"]
 
 
