@@ -53,6 +53,8 @@ SYMBOLS = [
     ("dtr_b200_set_stream", C.c_int, [C.c_void_p, C.c_void_p]),
     ("dtr_b200_set_band", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     ("dtr_b200_upload_texture", C.c_int, [C.c_void_p, _u8, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    ("dtr_b200_upload_bitmap_straight", C.c_int, [C.c_void_p, _u8, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    ("dtr_b200_read_texture", C.c_int, [C.c_void_p, C.c_int, _u8]),
     ("dtr_b200_upload_mesh", C.c_int, [C.c_void_p, C.POINTER(MeshDesc), C.c_int, C.POINTER(C.c_int)]),
     ("dtr_b200_set_target", C.c_int, [C.c_void_p, C.c_int]),
     ("dtr_b200_begin_frame", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -178,6 +180,19 @@ class Renderer:
         self._ck(self.lib.dtr_b200_upload_texture(self.ctx, a.ctypes.data_as(_u8), w, h, 4, C.byref(tid)))
         self._tex[key] = (tid.value, tex)
         return tid.value
+
+    def upload_bitmap_straight(self, rgba):
+        """Straight-alpha RGBA8 -> premultiplied texture (DTRAsset_LoadBitmap's pass, on the device)."""
+        a = np.ascontiguousarray(rgba, dtype=np.uint8)
+        h, w = a.shape[:2]
+        tid = C.c_int(-1)
+        self._ck(self.lib.dtr_b200_upload_bitmap_straight(self.ctx, a.ctypes.data_as(_u8), w, h, C.byref(tid)))
+        return tid.value
+
+    def read_texture(self, tex_id, shape):
+        out = np.empty(shape, np.uint8)
+        self._ck(self.lib.dtr_b200_read_texture(self.ctx, tex_id, out.ctypes.data_as(_u8)))
+        return out
 
     def upload_mesh(self, mesh, tex_id):
         key = (id(mesh), tex_id)
@@ -369,6 +384,12 @@ class Renderer:
         tid = self.upload_texture(tex)
         t = make_transform(transform)
         self._ck(self.lib.dtr_b200_bitmap(self.ctx, tid, _fp(_fa(pos, 2)), C.byref(t) if t else None,
+                                          _fp(_fa(color, 4))))
+
+    def bitmap_id(self, tex_id, pos, transform=None, color=(1, 1, 1, 1)):
+        """DTRRender_Bitmap with a texture that is already on the device (see upload_bitmap_straight)."""
+        t = make_transform(transform)
+        self._ck(self.lib.dtr_b200_bitmap(self.ctx, tex_id, _fp(_fa(pos, 2)), C.byref(t) if t else None,
                                           _fp(_fa(color, 4))))
 
     def line(self, a, b, color):

@@ -653,6 +653,27 @@ int dtr_b200_upload_texture(dtr_b200_ctx *c, const uint8_t *texels, int width, i
 	return DTR_B200_OK;
 }
 
+int dtr_b200_upload_bitmap_straight(dtr_b200_ctx *c, const uint8_t *rgba, int width, int height, int *texId)
+{
+	// upload the straight-alpha texels, then run DTRAsset_LoadBitmap's premultiply pass on the device
+	int rc = dtr_b200_upload_texture(c, rgba, width, height, 4, texId);
+	if (rc) return rc;
+	launch_premultiply(const_cast<uint32_t *>(c->textures[*texId].texels), (size_t)width * height, c->stream);
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(c->stream));
+	return DTR_B200_OK;
+}
+
+int dtr_b200_read_texture(dtr_b200_ctx *c, int texId, uint8_t *rgba)
+{
+	if (!c || !rgba) return DTR_B200_ERR_ARG;
+	if (texId < 0 || texId >= (int)c->textures.size()) return fail(c, DTR_B200_ERR_ARG, "texId out of range");
+	CU(cudaSetDevice(c->device));
+	const TexDesc &td = c->textures[texId];
+	CU(cudaMemcpy(rgba, td.texels, (size_t)td.w * td.h * 4, cudaMemcpyDeviceToHost));
+	return DTR_B200_OK;
+}
+
 int dtr_b200_upload_mesh(dtr_b200_ctx *c, const dtr_b200_mesh_desc *m, int texId, int *meshId)
 {
 	if (!c || !meshId) return DTR_B200_ERR_ARG;

@@ -90,5 +90,6 @@ void launch_tile_sum(const TileSumParams &P, cudaStream_t s);
 void launch_selftest_sqrt(unsigned long long *mismatches, cudaStream_t s);
 void launch_bin(const BinParams &P, cudaStream_t s);
 void launch_raster(const RasterParams &P, cudaStream_t s);
+void launch_premultiply(uint32_t *pixels, size_t count, cudaStream_t s);
 
 } // namespace dtr

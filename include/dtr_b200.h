@@ -118,6 +118,13 @@ int         dtr_b200_set_band(dtr_b200_ctx *ctx, int y0, int y1);
 /* ---- assets (device resident until destroy) ----------------------------------------------- */
 int dtr_b200_upload_texture(dtr_b200_ctx *ctx, const uint8_t *texels, int width, int height,
                             int bytesPerPixel /* must be 4 */, int *texId);
+/* The step before the hot path: DTRAsset_LoadBitmap's per-pixel pass
+ * (DTRendererAsset.cpp:816-843) on the device.  `rgba` is what stb_image hands the reference
+ * (straight alpha, R in the low byte, rows already flipped by stbi_set_flip_vertically_on_load);
+ * the stored texture is premultiplied in sRGB space, bit for bit what DTRBitmap::memory holds after
+ * DTRAsset_LoadBitmap.  dtr_b200_read_texture copies a texture back (tests, tools). */
+int dtr_b200_upload_bitmap_straight(dtr_b200_ctx *ctx, const uint8_t *rgba, int width, int height, int *texId);
+int dtr_b200_read_texture(dtr_b200_ctx *ctx, int texId, uint8_t *rgba);
 int dtr_b200_upload_mesh(dtr_b200_ctx *ctx, const dtr_b200_mesh_desc *mesh, int texId, int *meshId);
 
 /* ---- frame -------------------------------------------------------------------------------- */

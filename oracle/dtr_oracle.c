@@ -752,3 +752,26 @@ void dtro_text(dtro_ctx *c, const uint8_t *atlas, int atlasW, int atlasH, const 
 			}
 	}
 }
+
+void dtro_premultiply_bitmap(uint32_t *pixels, int count)
+{
+	/* DTRAsset_LoadBitmap's per-pixel pass (DTRendererAsset.cpp:823-841) with
+	 * DTRRender_PreMultiplyAlphaSRGB1WithLinearConversion (DTRendererRender.cpp:113-121):
+	 * byte * (1/255) [reciprocal multiply: the macro is the operand of operator*=], square,
+	 * times alpha, sqrtf (0 stays 0), * 255, truncate.  Alpha only goes through *(1/255)*255. */
+	const float INV_255 = 1.0f / 255.0f;
+	for (int i = 0; i < count; i++)
+	{
+		const uint32_t pixel = pixels[i];
+		float ch[4] = {(float)(pixel & 0xFF), (float)((pixel >> 8) & 0xFF), (float)((pixel >> 16) & 0xFF), (float)(pixel >> 24)};
+		for (int k = 0; k < 4; k++) ch[k] = ch[k] * INV_255;
+		for (int k = 0; k < 3; k++)
+		{
+			float v = ch[k] * ch[k];
+			v       = v * ch[3];
+			ch[k]   = (v == 0) ? 0 : sqrtf(v);
+		}
+		for (int k = 0; k < 4; k++) ch[k] = ch[k] * 255.0f;
+		pixels[i] = ((uint32_t)ch[3] << 24) | ((uint32_t)ch[2] << 16) | ((uint32_t)ch[1] << 8) | (uint32_t)ch[0];
+	}
+}

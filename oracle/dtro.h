@@ -71,6 +71,13 @@ typedef struct dtro_packedchar
 void dtro_text(dtro_ctx *c, const uint8_t *atlas, int atlasW, int atlasH, const dtro_packedchar *chars,
                int cpMin, int cpMax, const float pos[2], const char *text, const float color[4], int len);
 
+/* The per-pixel pass of DTRAsset_LoadBitmap (DTRendererAsset.cpp:816-843): straight-alpha RGBA8
+ * texels (R in the low byte, as stb_image returns them) -> premultiplied in sRGB space, in place.
+ * The reference build calls the renderer's own DTRRender_PreMultiplyAlphaSRGB1WithLinearConversion
+ * (DTRendererRender.cpp:113-121) inside the loop restated from the asset file (that file does not
+ * compile under g++). */
+void dtro_premultiply_bitmap(uint32_t *pixels, int count);
+
 #ifdef __cplusplus
 }
 #endif

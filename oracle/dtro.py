@@ -35,6 +35,15 @@ _u8 = C.POINTER(C.c_uint8)
 _i32 = C.POINTER(C.c_int32)
 
 
+def premultiply_bitmap(rgba, kind="port"):
+    """DTRAsset_LoadBitmap's premultiply pass on a copy of u8[..., 4] straight-alpha texels."""
+    lib = _load(kind)
+    a = np.ascontiguousarray(rgba, dtype=np.uint8).copy()
+    lib.dtro_premultiply_bitmap.argtypes = [C.c_void_p, C.c_int]
+    lib.dtro_premultiply_bitmap(a.ctypes.data_as(C.c_void_p), a.size // 4)
+    return a
+
+
 def available(kind):
     return os.path.exists(_PATHS[kind])
 

@@ -225,4 +225,26 @@ void dtro_text(dtro_ctx *c, const uint8_t *atlas, int atlasW, int atlasH, const 
 	DTRRender_Text(c->ctx, font, DqnV2_2f(pos[0], pos[1]), text, DqnV4_4f(color[0], color[1], color[2], color[3]), len);
 }
 
+void dtro_premultiply_bitmap(uint32_t *pixels, int count)
+{
+	for (int i = 0; i < count; i++)
+	{
+		// loop body of DTRAsset_LoadBitmap (DTRendererAsset.cpp:823-841), the reference's own helpers
+		u32   pixel = pixels[i];
+		DqnV4 color = {};
+		color.a     = (f32)(pixel >> 24);
+		color.b     = (f32)((pixel >> 16) & 0xFF);
+		color.g     = (f32)((pixel >> 8) & 0xFF);
+		color.r     = (f32)((pixel >> 0) & 0xFF);
+
+		DqnV4 preMulColor = color;
+		preMulColor *= DTRRENDER_INV_255;
+		preMulColor = DTRRender_PreMultiplyAlphaSRGB1WithLinearConversion(preMulColor);
+		preMulColor *= 255.0f;
+
+		pixels[i] = (((u32)preMulColor.a << 24) | ((u32)preMulColor.b << 16) | ((u32)preMulColor.g << 8) |
+		             ((u32)preMulColor.r << 0));
+	}
+}
+
 } // extern "C"

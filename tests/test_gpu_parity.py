@@ -390,3 +390,25 @@ def test_debug_marker_overlay_matches_reference_default_build(built):
     col, z = r.end_frame(0)
     _assert_same(col, z, o.color(), o.zbuffer())
     assert r.stats()["setPixels"] == o.counters()[0]
+
+
+def test_device_premultiply_matches_asset_loader_pass(built):
+    """straight-alpha upload + device premultiply == DTRAsset_LoadBitmap's pass,
+    over every (channel value, alpha) pair; and a bitmap drawn from it equals the oracle's."""
+    from oracle import dtro
+    kind = "reference" if dtro.available("reference") else "port"
+    v, a = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8))
+    rgba = np.ascontiguousarray(np.stack([v, v[::-1], v.T, a], -1))
+    want = dtro.premultiply_bitmap(rgba, kind)
+    r = _renderer(320, 300)
+    tid = r.upload_bitmap_straight(rgba)
+    assert np.array_equal(r.read_texture(tid, rgba.shape), want)
+    o = _oracle(320, 300)
+    r.begin_frame(0)
+    for t in (o, r):
+        t.clear((0.3, 0.6, 0.2))
+    tr = scenes.transform7(0.2, (0.5, 0.5, 0.0), (1.1, 0.9, 1.0))
+    o.bitmap(want, (20.0, 15.0), tr, (1.0, 0.9, 0.8, 0.9))
+    r.bitmap_id(tid, (20.0, 15.0), tr, (1.0, 0.9, 0.8, 0.9))
+    col, z = r.end_frame(0)
+    _assert_same(col, z, o.color(), o.zbuffer())
