@@ -28,11 +28,11 @@ constexpr int RASTER_THREADS = 128;
 #define DTR_RASTER_CTAS 5
 #endif
 #ifndef DTR_RASTER_TAIL
-#define DTR_RASTER_TAIL 25
+#define DTR_RASTER_TAIL 10
 #endif
 constexpr int RASTER_TAIL_PERCENT = DTR_RASTER_TAIL; // share of the untouched tiles kept for the end of the launch
 #ifndef DTR_RASTER_SMALL
-#define DTR_RASTER_SMALL 10
+#define DTR_RASTER_SMALL 5
 #endif
 constexpr int RASTER_SMALL_PERCENT = DTR_RASTER_SMALL; // share of the busy tiles rasterised as four 32x16 items
 constexpr int RASTER_CTAS_PER_SM = DTR_RASTER_CTAS; // 5 x 4 warps per SM, each warp with 10.4 KB of shared memory
