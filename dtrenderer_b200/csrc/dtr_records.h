@@ -18,9 +18,12 @@ namespace dtr
 // single warps; a region is 32 sub-blocks of 8x4 pixels (one sub-block per lane when a triangle is
 // classified against the region, one pixel per lane when a sub-block is rasterised).
 constexpr int TILE_W      = 64;
-constexpr int TILE_H      = 32;
+#ifndef DTR_TILE_H
+#define DTR_TILE_H 32
+#endif
+constexpr int TILE_H      = DTR_TILE_H; // 32, or 24 (divides 1080 and 2160; 6 CTAs per SM fit)
 constexpr int REGION_W    = 32;
-constexpr int REGION_H    = 32;
+constexpr int REGION_H    = TILE_H;
 constexpr int SUB_W       = 8;
 constexpr int SUB_H       = 4;
 constexpr int RASTER_THREADS = 128;
