@@ -2,7 +2,7 @@
 //
 // Host side of the back end: records draw calls, evaluates the once-per-call host arithmetic
 // (dtr_host_math.h), uploads one command block per flush and launches
-//     setup_kernel -> scan_kernel -> bin_kernel -> raster_kernel
+//     setup_kernel -> (tile_sum_kernel) -> scan_kernel -> bin_rows_kernel -> raster_kernel
 // on the context's stream.  There is no CPU rendering path in this file: if CUDA is not
 // available dtr_b200_create fails.  Compiled with -ffp-contract=off.
 #include <cuda_runtime_api.h>
