@@ -412,3 +412,77 @@ def test_device_premultiply_matches_asset_loader_pass(built):
     r.bitmap_id(tid, (20.0, 15.0), tr, (1.0, 0.9, 0.8, 0.9))
     col, z = r.end_frame(0)
     _assert_same(col, z, o.color(), o.zbuffer())
+
+
+@pytest.mark.parametrize("seed,size", [(1, (257, 131)), (2, (640, 360)), (3, (96, 1000)), (4, (1023, 65))])
+def test_fuzz_mixed_primitives(built, seed, size):
+    """Random interleavings of every primitive kind (exact and transformed triangles, textured
+    triangles, mesh, rectangles, bitmaps, lines, text, clears in mid-frame) at awkward sizes, split
+    over random flushes: the device frame, depth and SetPixels counter equal the oracle's."""
+    rng = np.random.default_rng(1000 + seed)
+    w, h = size
+    texs = [scenes.random_texture(int(rng.integers(2, 48)), int(rng.integers(2, 48)), 10 + i, opaque=bool(i & 1)) for i in range(3)]
+    font = scenes.synthetic_font(20 + seed)
+    mesh = scenes.uv_sphere(14, 7)
+    o, r = _oracle(w, h), _renderer(w, h)
+    o.reset_counters()
+    r.begin_frame(0)
+    both = (o, r)
+    for t in both:
+        t.clear((0.2, 0.5, 0.4))
+    for i in range(140):
+        kind = int(rng.integers(0, 9))
+        col = (*rng.random(3).tolist(), float(rng.choice([1.0, rng.random()])))
+        tr = scenes.transform7(float(rng.uniform(-3, 3)) if rng.random() < 0.5 else 0.0, (*rng.random(2), 0.0),
+                               (float(rng.uniform(0.4, 2.5)), float(rng.uniform(0.4, 2.5)), 1.0))
+        if kind == 0:      # integer-vertex triangles (exact path), a small batch
+            n = int(rng.integers(1, 40))
+            c = rng.integers(-10, [w + 10, h + 10], (n, 1, 2))
+            p = np.concatenate([c + rng.integers(-30, 31, (n, 3, 2)), rng.uniform(0, 255, (n, 3, 1))], 2).astype(np.float32)
+            cols = rng.random((n, 4)).astype(np.float32)
+            cols[rng.random(n) < 0.6, 3] = 1.0
+            for t in both:
+                t.triangles(p.reshape(n, 9), cols, scenes.DEFAULT_TRIANGLE_TRANSFORM)
+        elif kind == 1:    # transformed triangle (sequential-accumulation path)
+            p = np.concatenate([rng.uniform(-40, [w + 40, h + 40], (3, 2)), rng.uniform(0, 255, (3, 1))], 1).astype(np.float32)
+            tri_tr = scenes.transform7(tr[0], tuple(rng.random(3)), (tr[4], tr[5], 1.0))
+            for t in both:
+                t.triangle(p.reshape(-1), col, tri_tr)
+        elif kind == 2:
+            p = np.concatenate([rng.integers(-20, [w + 20, h + 20], (3, 2)), rng.uniform(0, 255, (3, 1))], 1).astype(np.float32)
+            uv = (rng.random(6) * 0.999).astype(np.float32)
+            for t in both:
+                t.textured_triangle(p.reshape(-1), uv, texs[i % 3], col, scenes.DEFAULT_TRIANGLE_TRANSFORM)
+        elif kind == 3:
+            mn = rng.uniform(-30, [w, h]).astype(np.float32)
+            mx = mn + rng.uniform(1, 120, 2).astype(np.float32)
+            for t in both:
+                t.rectangle(mn, mx, col, tr)
+        elif kind == 4:
+            pos = rng.uniform(-30, [w, h]).astype(np.float32)
+            for t in both:
+                t.bitmap(texs[i % 3], pos, tr, col)
+        elif kind == 5:
+            a = rng.integers(-20, [w + 20, h + 20]).astype(np.int32)
+            b = rng.integers(-20, [w + 20, h + 20]).astype(np.int32)
+            for t in both:
+                t.line(a, b, col)
+        elif kind == 6:
+            s = bytes(rng.integers(32, 127, int(rng.integers(1, 16))).astype(np.uint8))
+            pos = rng.uniform(-15, [w, h + 8]).astype(np.float32)
+            for t in both:
+                t.text(font, pos, s, col)
+        elif kind == 7 and i % 3 == 0:
+            mode = int(rng.integers(0, 3))
+            view = scenes.view_transforms(4096)[int(rng.integers(0, 4096))]
+            for t in both:
+                t.mesh(mesh, texs[1], mode, (1, -1, 1), (1, 1, 1, 1), (0.1, 0.0, 0.0), view)
+        elif kind == 8 and rng.random() < 0.15:
+            rgb = tuple(rng.random(3))
+            for t in both:
+                t.clear(rgb)
+        if rng.random() < 0.1:
+            r.flush()
+    col_, z_ = r.end_frame(0)
+    _assert_same(col_, z_, o.color(), o.zbuffer())
+    assert r.stats()["setPixels"] == o.counters()[0]
