@@ -294,6 +294,15 @@ def run_gpu_arm(args, rank, world, local_rank):
     ms = e0.elapsed_time(e1)
     stage, runs = r.stage_ms()
     launches = r.stats()["kernelLaunches"]
+    # untimed extra pass with the replay pipelining off: per-stage times in isolation (in the timed
+    # region the pre-raster stages of replay i+1 overlap the raster kernel of replay i, so their
+    # event intervals include the wait for free SMs and the stages no longer add up to the step)
+    r.set_replay_overlap(False)
+    r.reset_stage_ms()
+    for _ in range(10):
+        r.replay()
+    stage_iso, runs_iso = r.stage_ms()
+    r.set_replay_overlap(True)
     r.set_profiling(False)
     t = torch.tensor([ms], device="cuda")
     if world > 1:
@@ -349,7 +358,12 @@ def run_gpu_arm(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": "raster_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": raster_ms,
-                         "stage_ms_per_step": {k: v / max(runs, 1) for k, v in stage.items()}},
+                         "stage_ms_per_step": {k: v / max(runs, 1) for k, v in stage.items()},
+                         "stage_ms_isolated": {k: v / max(runs_iso, 1) for k, v in stage_iso.items()},
+                         "note": "achieved/frac use the raster kernel's duration inside the timed region, where "
+                                 "setup/scan/bin of the next replay run on a second stream during its tail (their "
+                                 "stage_ms_per_step therefore include waiting for SMs); stage_ms_isolated = the same "
+                                 "stages timed in an extra pass with that pipelining off"},
             "cpu_baseline": cpu,
             "e2e": {"value": world * shaded_per_step / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
                     "h2d_bytes_per_step": upload_bytes, "d2h_bytes_per_step": B * 4 * w * h,

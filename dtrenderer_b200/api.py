@@ -60,6 +60,7 @@ SYMBOLS = [
     ("dtr_b200_begin_frame", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     ("dtr_b200_flush", C.c_int, [C.c_void_p]),
     ("dtr_b200_replay", C.c_int, [C.c_void_p]),
+    ("dtr_b200_set_replay_overlap", C.c_int, [C.c_void_p, C.c_int]),
     ("dtr_b200_sync", C.c_int, [C.c_void_p]),
     ("dtr_b200_end_frame", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     ("dtr_b200_read_frames", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -221,6 +222,9 @@ class Renderer:
 
     def replay(self):
         self._ck(self.lib.dtr_b200_replay(self.ctx))
+
+    def set_replay_overlap(self, enable=True):
+        self._ck(self.lib.dtr_b200_set_replay_overlap(self.ctx, 1 if enable else 0))
 
     def sync(self):
         self._ck(self.lib.dtr_b200_sync(self.ctx))

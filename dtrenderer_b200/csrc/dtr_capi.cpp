@@ -100,11 +100,25 @@ struct dtr_b200_ctx
 	std::vector<uint8_t>   texIsWhite; // every texel 0xFFFFFFFF: sampling multiplies by exactly 1.0f
 	DevBuf                 dTextures;
 
-	DevBuf dCmd, dPayload, dPrims, dBounds, dTileCount, dTileOffset, dOrder, dLists, dSegRel;
-	unsigned long long *dSetPixels = nullptr; // [0] SetPixel count, [1] list total, [2] unused, [3] work counter, [4] busy tiles
+	DevBuf dCmd, dPayload;
+	// Intermediate buffers of one pass of the pipeline.  Two sets: a flush uses set 0; replays
+	// alternate, so that setup / scan / bin of replay i+1 (on preStream) can run while the raster
+	// kernel of replay i is still finishing on the main stream.
+	struct PipeSet
+	{
+		DevBuf              prims, bounds, tileCount, tileOffset, order, lists, segRel;
+		unsigned long long *counters = nullptr; // [1] list total, [3] work counter, [4] busy tiles
+		cudaEvent_t         preDone = nullptr, rasterDone = nullptr;
+		bool                rasterPending = false; // rasterDone has been recorded: the set may still be read
+	};
+	PipeSet             sets[2];
+	int                 nextReplaySet = 1;
+	bool                replayOverlap = true; // dtr_b200_set_replay_overlap
+	cudaStream_t        preStream = nullptr;
+	unsigned long long *dSetPixels = nullptr; // [0] SetPixel count of every raster launch so far
 	uint64_t            triangles = 0, launches = 0, uploadBytes = 0;
 	bool                     profiling = false;
-	std::vector<cudaEvent_t> events;     // 5 per profiled pipeline
+	std::vector<cudaEvent_t> events;     // EVENTS_PER_RUN per profiled pipeline
 	std::vector<cudaEvent_t> eventPool;  // recycled
 
 	// last flush, for replay
@@ -251,9 +265,11 @@ int record_tris(dtr_b200_ctx *c, int n, const float *p, const float *color, cons
 	return 0;
 }
 
-int mark(dtr_b200_ctx *c)
+constexpr int EVENTS_PER_RUN = 6; // pre start, after setup, after scan, after bin | raster start, raster end
+
+int mark(dtr_b200_ctx *c, cudaStream_t stream)
 {
-	if (!c->profiling || c->events.size() >= 5 * 8192) return 0;
+	if (!c->profiling || c->events.size() >= (size_t)EVENTS_PER_RUN * 8192) return 0;
 	cudaEvent_t e;
 	if (!c->eventPool.empty())
 	{
@@ -261,7 +277,7 @@ int mark(dtr_b200_ctx *c)
 		c->eventPool.pop_back();
 	}
 	else CU(cudaEventCreate(&e));
-	CU(cudaEventRecord(e, c->stream));
+	CU(cudaEventRecord(e, stream));
 	c->events.push_back(e);
 	return 0;
 }
@@ -280,112 +296,131 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	const DrawItem   *dItems  = (const DrawItem *)((const uint8_t *)c->dCmd.p + sizeof(FrameState) * numActive);
 	const uint32_t   *dBlockItem = (const uint32_t *)(dItems + numItems);
 
+	// A flush runs everything on the main stream with buffer set 0 (it has to wait for the list
+	// total on the host anyway).  A replay takes the other set in turn and runs setup / scan / bin on
+	// preStream: they only touch the set's buffers, so they may overlap the previous raster kernel,
+	// whose tail leaves SMs idle; the raster kernels themselves stay ordered on the main stream.
+	const bool             overlap = replay && c->replayOverlap;
+	dtr_b200_ctx::PipeSet &S   = c->sets[overlap ? c->nextReplaySet : 0];
+	const cudaStream_t     pre = overlap ? c->preStream : c->stream;
+	if (overlap) c->nextReplaySet ^= 1;
+	else if (replay) CU(cudaStreamSynchronize(c->preStream)); // set 0 may be in use by an overlapped replay
+	if (S.rasterPending && pre != c->stream) CU(cudaStreamWaitEvent(pre, S.rasterDone, 0));
+
 	int rc;
 	// one buffer, one memset: (tile, segment) counts | per-tile counts (segs > 1 only) | look-back words
 	const size_t tileWords   = g.segs > 1 ? (size_t)numTiles : 0;
 	const size_t countWords  = (numSeg + tileWords + 1) & ~(size_t)1; // keep the 64-bit words aligned
 	const size_t statusWords = scan_status_words(numTiles);
-	if ((rc = ensure_dev(c, c->dTileCount, sizeof(uint32_t) * countWords + sizeof(unsigned long long) * statusWords))) return rc;
-	if ((rc = ensure_dev(c, c->dOrder, sizeof(uint32_t) * std::max<size_t>(numTiles, 1)))) return rc;
-	if ((rc = ensure_dev(c, c->dTileOffset, sizeof(uint32_t) * ((size_t)numTiles + 1)))) return rc;
-	if ((rc = ensure_dev(c, c->dSegRel, sizeof(uint32_t) * std::max<size_t>(g.segs > 1 ? numSeg : 1, 1)))) return rc;
-	if ((rc = ensure_dev(c, c->dPrims, sizeof(PrimRecord) * (size_t)std::max(numPrims, 1u)))) return rc;
-	if ((rc = ensure_dev(c, c->dBounds, sizeof(PrimBounds) * (size_t)std::max(numPrims, 1u)))) return rc;
-	uint32_t *dSegCount  = (uint32_t *)c->dTileCount.p;
+	if ((rc = ensure_dev(c, S.tileCount, sizeof(uint32_t) * countWords + sizeof(unsigned long long) * statusWords))) return rc;
+	if ((rc = ensure_dev(c, S.order, sizeof(uint32_t) * std::max<size_t>(numTiles, 1)))) return rc;
+	if ((rc = ensure_dev(c, S.tileOffset, sizeof(uint32_t) * ((size_t)numTiles + 1)))) return rc;
+	if ((rc = ensure_dev(c, S.segRel, sizeof(uint32_t) * std::max<size_t>(g.segs > 1 ? numSeg : 1, 1)))) return rc;
+	if ((rc = ensure_dev(c, S.prims, sizeof(PrimRecord) * (size_t)std::max(numPrims, 1u)))) return rc;
+	if ((rc = ensure_dev(c, S.bounds, sizeof(PrimBounds) * (size_t)std::max(numPrims, 1u)))) return rc;
+	uint32_t *dSegCount  = (uint32_t *)S.tileCount.p;
 	uint32_t *dTileCount = g.segs > 1 ? dSegCount + numSeg : dSegCount; // with one segment they are the same thing
 
 	unsigned long long *dScanStatus = (unsigned long long *)(dSegCount + countWords);
-	CU(cudaMemsetAsync(dSegCount, 0, sizeof(uint32_t) * countWords + sizeof(unsigned long long) * statusWords, c->stream));
-	if ((rc = mark(c))) return rc;
+	if ((rc = mark(c, pre))) return rc;
+	CU(cudaMemsetAsync(dSegCount, 0, sizeof(uint32_t) * countWords + sizeof(unsigned long long) * statusWords, pre));
 	if (numPrims)
 	{
-		SetupParams S;
-		S.items       = dItems;
-		S.blockItem   = dBlockItem;
-		S.numItems    = (int)numItems;
-		S.numPrims    = numPrims;
-		S.prims       = (PrimRecord *)c->dPrims.p;
-		S.bounds      = (PrimBounds *)c->dBounds.p;
-		S.segCount    = dSegCount;
-		S.frames      = dFrames;
-		S.textures    = (const TexDesc *)c->dTextures.p;
-		S.g           = g;
-		launch_setup(S, c->stream);
+		SetupParams SP;
+		SP.items       = dItems;
+		SP.blockItem   = dBlockItem;
+		SP.numItems    = (int)numItems;
+		SP.numPrims    = numPrims;
+		SP.prims       = (PrimRecord *)S.prims.p;
+		SP.bounds      = (PrimBounds *)S.bounds.p;
+		SP.segCount    = dSegCount;
+		SP.frames      = dFrames;
+		SP.textures    = (const TexDesc *)c->dTextures.p;
+		SP.g           = g;
+		launch_setup(SP, pre);
 		c->launches++;
 	}
-	if ((rc = mark(c))) return rc;
+	if ((rc = mark(c, pre))) return rc;
 	if (g.segs > 1)
 	{
 		TileSumParams TS;
 		TS.segCount  = dSegCount;
-		TS.segRel    = (uint32_t *)c->dSegRel.p;
+		TS.segRel    = (uint32_t *)S.segRel.p;
 		TS.tileCount = dTileCount;
 		TS.numTiles  = numTiles;
 		TS.segs      = (uint32_t)g.segs;
-		launch_tile_sum(TS, c->stream);
+		launch_tile_sum(TS, pre);
 		c->launches++;
 	}
 	ScanParams SC;
 	SC.counts      = dTileCount;
-	SC.offsets     = (uint32_t *)c->dTileOffset.p;
+	SC.offsets     = (uint32_t *)S.tileOffset.p;
 	SC.n           = numTiles;
-	SC.order       = (uint32_t *)c->dOrder.p;
+	SC.order       = (uint32_t *)S.order.p;
 	SC.status      = dScanStatus;
-	SC.totals      = c->dSetPixels + 1;
-	SC.workCounter = (uint32_t *)(c->dSetPixels + 3);
-	SC.numBusy     = (uint32_t *)(c->dSetPixels + 4);
-	launch_scan(SC, c->stream);
+	SC.totals      = S.counters + 1;
+	SC.workCounter = (uint32_t *)(S.counters + 3);
+	SC.numBusy     = (uint32_t *)(S.counters + 4);
+	launch_scan(SC, pre);
 	c->launches++;
-	if ((rc = mark(c))) return rc;
+	if ((rc = mark(c, pre))) return rc;
 
 	uint64_t total = c->last.listTotal;
 	if (!replay)
 	{
 		unsigned long long t = 0;
-		CU(cudaMemcpyAsync(&t, c->dSetPixels + 1, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
-		CU(cudaStreamSynchronize(c->stream));
+		CU(cudaMemcpyAsync(&t, S.counters + 1, sizeof(t), cudaMemcpyDeviceToHost, pre));
+		CU(cudaStreamSynchronize(pre));
 		total = t;
 		if (total >= (1ull << 31)) return fail(c, DTR_B200_ERR_OVERFLOW, "more than 2^31 (primitive, tile) pairs in one flush");
-		if ((rc = ensure_dev(c, c->dLists, sizeof(uint32_t) * (size_t)std::max<uint64_t>(total, 1)))) return rc;
 	}
+	if ((rc = ensure_dev(c, S.lists, sizeof(uint32_t) * (size_t)std::max<uint64_t>(total, 1)))) return rc;
 
 	if (numPrims && total)
 	{
 		BinParams B;
-		B.bounds       = (const PrimBounds *)c->dBounds.p;
+		B.bounds       = (const PrimBounds *)S.bounds.p;
 		B.frames       = dFrames;
 		B.segCount     = dSegCount;
-		B.segRel       = (const uint32_t *)c->dSegRel.p;
-		B.tileOffset   = (const uint32_t *)c->dTileOffset.p;
-		B.lists        = (uint32_t *)c->dLists.p;
-		B.listCapacity = (uint32_t)(c->dLists.cap / sizeof(uint32_t));
+		B.segRel       = (const uint32_t *)S.segRel.p;
+		B.tileOffset   = (const uint32_t *)S.tileOffset.p;
+		B.lists        = (uint32_t *)S.lists.p;
+		B.listCapacity = (uint32_t)(S.lists.cap / sizeof(uint32_t));
 		B.groupRows    = 0;
 		B.g            = g;
-		launch_bin(B, c->stream);
+		launch_bin(B, pre);
 		c->launches++;
 	}
-	if ((rc = mark(c))) return rc;
+	if ((rc = mark(c, pre))) return rc;
+	if (pre != c->stream)
+	{
+		CU(cudaEventRecord(S.preDone, pre));
+		CU(cudaStreamWaitEvent(c->stream, S.preDone, 0));
+	}
 
 	RasterParams R;
 	R.color      = c->outColor;
 	R.depth      = c->outDepth;
 	R.frames     = dFrames;
-	R.prims      = (const PrimRecord *)c->dPrims.p;
-	R.bounds     = (const PrimBounds *)c->dBounds.p;
+	R.prims      = (const PrimRecord *)S.prims.p;
+	R.bounds     = (const PrimBounds *)S.bounds.p;
 	R.tileCount  = dTileCount;
-	R.tileOffset = (const uint32_t *)c->dTileOffset.p;
-	R.order      = (const uint32_t *)c->dOrder.p;
-	R.lists      = (const uint32_t *)c->dLists.p;
+	R.tileOffset = (const uint32_t *)S.tileOffset.p;
+	R.order      = (const uint32_t *)S.order.p;
+	R.lists      = (const uint32_t *)S.lists.p;
 	R.textures   = (const TexDesc *)c->dTextures.p;
 	R.setPixels  = c->dSetPixels;
-	R.workCounter    = (uint32_t *)(c->dSetPixels + 3);
-	R.numBusy        = (const uint32_t *)(c->dSetPixels + 4);
+	R.workCounter    = (uint32_t *)(S.counters + 3);
+	R.numBusy        = (const uint32_t *)(S.counters + 4);
 	R.numTiles       = 0;
 	R.smallTilesMin  = 0;
 	R.g          = g;
+	if ((rc = mark(c, c->stream))) return rc;
 	launch_raster(R, c->stream);
 	c->launches++;
-	if ((rc = mark(c))) return rc;
+	if ((rc = mark(c, c->stream))) return rc;
+	CU(cudaEventRecord(S.rasterDone, c->stream));
+	S.rasterPending = true;
 	CU(cudaGetLastError());
 
 	c->last.valid     = true;
@@ -410,6 +445,10 @@ int do_flush(dtr_b200_ctx *c)
 			active.push_back((uint32_t)f);
 		}
 	if (active.empty()) return 0;
+	// replays may still be running their pre-raster stages on preStream; a flush rewrites the
+	// command block they read
+	CU(cudaStreamSynchronize(c->preStream));
+	CU(cudaStreamSynchronize(c->stream));
 	if (c->readHi > c->readLo)
 	{
 		// a frame that is still being read back must not be overwritten
@@ -539,6 +578,7 @@ int dtr_b200_create(int device, int width, int height, int numFrames, dtr_b200_c
 	    (e = cudaEventCreateWithFlags(&n->copyDone, cudaEventDisableTiming)) != cudaSuccess ||
 	    (e = cudaMalloc((void **)&n->dColor, plane * numFrames * sizeof(uint32_t))) != cudaSuccess ||
 	    (e = cudaMalloc((void **)&n->dDepth, plane * numFrames * sizeof(float))) != cudaSuccess ||
+	    (e = cudaStreamCreateWithFlags(&n->preStream, cudaStreamNonBlocking)) != cudaSuccess ||
 	    (e = cudaMalloc((void **)&n->dSetPixels, 8 * sizeof(unsigned long long))) != cudaSuccess ||
 	    (e = cudaMemset(n->dColor, 0, plane * numFrames * sizeof(uint32_t))) != cudaSuccess ||
 	    (e = cudaMemset(n->dSetPixels, 0, 8 * sizeof(unsigned long long))) != cudaSuccess)
@@ -546,6 +586,18 @@ int dtr_b200_create(int device, int width, int height, int numFrames, dtr_b200_c
 		fail(nullptr, DTR_B200_ERR_CUDA, "allocating frame targets", e);
 		dtr_b200_destroy(n);
 		return DTR_B200_ERR_CUDA;
+	}
+	for (auto &ps : n->sets)
+	{
+		if ((e = cudaMalloc((void **)&ps.counters, 8 * sizeof(unsigned long long))) != cudaSuccess ||
+		    (e = cudaMemset(ps.counters, 0, 8 * sizeof(unsigned long long))) != cudaSuccess ||
+		    (e = cudaEventCreateWithFlags(&ps.preDone, cudaEventDisableTiming)) != cudaSuccess ||
+		    (e = cudaEventCreateWithFlags(&ps.rasterDone, cudaEventDisableTiming)) != cudaSuccess)
+		{
+			fail(nullptr, DTR_B200_ERR_CUDA, "allocating pipeline state", e);
+			dtr_b200_destroy(n);
+			return DTR_B200_ERR_CUDA;
+		}
 	}
 	n->stream = n->ownStream;
 	n->outColor = n->dColor;
@@ -571,8 +623,15 @@ void dtr_b200_destroy(dtr_b200_ctx *c)
 	}
 	for (auto &t : c->textures) cudaFree((void *)t.texels);
 	for (auto &f : c->fonts) cudaFree(f.dAtlas);
-	DevBuf *bufs[] = {&c->dTextures, &c->dCmd, &c->dPayload, &c->dPrims, &c->dBounds, &c->dTileCount, &c->dTileOffset, &c->dOrder, &c->dLists,
-	                  &c->dSegRel};
+	if (c->preStream) cudaStreamSynchronize(c->preStream);
+	std::vector<DevBuf *> bufs = {&c->dTextures, &c->dCmd, &c->dPayload};
+	for (auto &ps : c->sets)
+	{
+		for (DevBuf *b : {&ps.prims, &ps.bounds, &ps.tileCount, &ps.tileOffset, &ps.order, &ps.lists, &ps.segRel}) bufs.push_back(b);
+		cudaFree(ps.counters);
+		if (ps.preDone) cudaEventDestroy(ps.preDone);
+		if (ps.rasterDone) cudaEventDestroy(ps.rasterDone);
+	}
 	for (DevBuf *b : bufs) cudaFree(b->p);
 	if (c->ipcColor) cudaIpcCloseMemHandle(c->ipcColor);
 	if (c->ipcDepth) cudaIpcCloseMemHandle(c->ipcDepth);
@@ -590,6 +649,7 @@ void dtr_b200_destroy(dtr_b200_ctx *c)
 	}
 	if (c->renderDone) cudaEventDestroy(c->renderDone);
 	if (c->copyDone) cudaEventDestroy(c->copyDone);
+	if (c->preStream) cudaStreamDestroy(c->preStream);
 	if (c->ownStream) cudaStreamDestroy(c->ownStream);
 	delete c;
 }
@@ -747,6 +807,16 @@ int dtr_b200_replay(dtr_b200_ctx *c)
 	if (!c->rec.empty()) return fail(c, DTR_B200_ERR_ARG, "replay with unflushed draw calls pending");
 	CU(cudaSetDevice(c->device));
 	return run_pipeline(c, c->last.numActive, c->last.numItems, c->last.numPrims, c->last.maxFramePrims, true);
+}
+
+int dtr_b200_set_replay_overlap(dtr_b200_ctx *c, int enable)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->preStream));
+	CU(cudaStreamSynchronize(c->stream));
+	c->replayOverlap = enable != 0;
+	return DTR_B200_OK;
 }
 
 int dtr_b200_sync(dtr_b200_ctx *c)
@@ -948,14 +1018,23 @@ int dtr_b200_get_stage_ms(dtr_b200_ctx *c, float ms[4], int *runs)
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->stream));
 	ms[0] = ms[1] = ms[2] = ms[3] = 0.0f;
-	*runs = (int)(c->events.size() / 5);
+	CU(cudaStreamSynchronize(c->preStream));
+	*runs = (int)(c->events.size() / EVENTS_PER_RUN);
 	for (int r = 0; r < *runs; r++)
-		for (int s = 0; s < 4; s++)
+	{
+		// setup, scan, bin: consecutive events on the stream that ran them; raster: its own pair of
+		// events on the main stream (with pipelined replays the raster kernel may start long after bin)
+		const cudaEvent_t *ev = &c->events[(size_t)EVENTS_PER_RUN * r];
+		for (int s2 = 0; s2 < 3; s2++)
 		{
 			float t = 0.0f;
-			CU(cudaEventElapsedTime(&t, c->events[5 * r + s], c->events[5 * r + s + 1]));
-			ms[s] += t;
+			CU(cudaEventElapsedTime(&t, ev[s2], ev[s2 + 1]));
+			ms[s2] += t;
 		}
+		float t = 0.0f;
+		CU(cudaEventElapsedTime(&t, ev[4], ev[5]));
+		ms[3] += t;
+	}
 	return DTR_B200_OK;
 }
 

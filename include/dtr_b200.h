@@ -138,6 +138,12 @@ int dtr_b200_flush(dtr_b200_ctx *ctx);
 /* Re-execute the last flushed command list from its device-resident copy (no host->device
  * traffic): every frame it touched is re-initialised the way it was before that flush. */
 int dtr_b200_replay(dtr_b200_ctx *ctx);
+/* Consecutive replays are pipelined by default: setup / scan / bin of replay i+1 run on a second
+ * stream with their own buffer set while the raster kernel of replay i is finishing (its tail
+ * leaves SMs idle); the raster kernels stay ordered.  Results are unaffected.  Disable (0) to time
+ * the stages in isolation: with the overlap on, the per-stage times of dtr_b200_get_stage_ms
+ * include the time a stage waited for free SMs. */
+int dtr_b200_set_replay_overlap(dtr_b200_ctx *ctx, int enable);
 int dtr_b200_sync(dtr_b200_ctx *ctx);
 /* Flush, then copy the frame back (either pointer may be NULL) and wait for it. */
 int dtr_b200_end_frame(dtr_b200_ctx *ctx, int frame, uint32_t *hostColor, float *hostZ);
@@ -174,7 +180,7 @@ int dtr_b200_get_stats(dtr_b200_ctx *ctx, dtr_b200_stats *out); /* syncs */
 int dtr_b200_reset_stats(dtr_b200_ctx *ctx);
 /* Per-stage device timing with CUDA events on the context's stream (the ncu/nsys replacement of
  * the reference's rdtsc region counters, DTRendererDebug.h:42-78).  While enabled, every
- * flush/replay records 5 events; dtr_b200_get_stage_ms syncs and returns the SUMS in ms of
+ * flush/replay records 6 events; dtr_b200_get_stage_ms syncs and returns the SUMS in ms of
  * {setup, scan, bin, raster} over the pipelines run since the last reset, and their number. */
 int dtr_b200_set_profiling(dtr_b200_ctx *ctx, int enable);
 int dtr_b200_get_stage_ms(dtr_b200_ctx *ctx, float ms[4], int *runs);

@@ -167,6 +167,27 @@ def test_frame_batch_views_and_replay(built):
     for f in range(n):
         col, z = r.end_frame(f)
         assert np.array_equal(col, first[f][0]) and np.array_equal(z.view(np.uint32), first[f][1].view(np.uint32))
+    # pipelined replays (pre-raster stages of replay i+1 overlap the raster kernel of replay i on a
+    # second stream with a second buffer set), with and without the overlap, and a flush in between
+    sp0 = r.stats()["setPixels"]
+    for _ in range(5):
+        r.replay()
+    r.set_replay_overlap(False)
+    for _ in range(2):
+        r.replay()
+    r.set_replay_overlap(True)
+    assert r.stats()["setPixels"] == sp0 + 7 * total
+    for f in range(n):
+        col, z = r.end_frame(f)
+        assert np.array_equal(col, first[f][0]) and np.array_equal(z.view(np.uint32), first[f][1].view(np.uint32))
+    r.begin_frame(0)
+    r.clear((0.5, 0.0, 1.0))
+    r.mesh(mesh, tex, scenes.SHADE_GOURAUD, (1, -1, 1), (1, 1, 1, 1), (0, 0, 0), ts[0])
+    r.flush()
+    for _ in range(3):
+        r.replay()
+    col, z = r.end_frame(0)
+    assert np.array_equal(col, first[0][0]) and np.array_equal(z.view(np.uint32), first[0][1].view(np.uint32))
 
 
 def test_band_split_equals_full_frame(built):
