@@ -127,6 +127,7 @@ struct dtr_b200_ctx
 		bool     valid = false;
 		uint32_t numActive = 0, numItems = 0, numPrims = 0, maxFramePrims = 0;
 		uint64_t listTotal = 0, triangles = 0;
+		bool     anyTextured = false; // some triangle item of the flush samples a (non-white) texture
 		Geometry g{};
 	} last;
 
@@ -412,6 +413,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	R.setPixels  = c->dSetPixels;
 	R.workCounter    = (uint32_t *)(S.counters + 3);
 	R.numBusy        = (const uint32_t *)(S.counters + 4);
+	R.anyTextured    = c->last.anyTextured ? 1u : 0u;
 	R.numTiles       = 0;
 	R.smallTilesMin  = 0;
 	R.g          = g;
@@ -524,6 +526,8 @@ int do_flush(dtr_b200_ctx *c)
 	if (c->payloadUsed)
 		CU(cudaMemcpyAsync(c->dPayload.p, c->payload, c->payloadUsed, cudaMemcpyHostToDevice, c->stream));
 
+	c->last.anyTextured = false;
+	for (uint32_t i = 0; i < numItems; i++) c->last.anyTextured = c->last.anyTextured || (it[i].type != ITEM_RAW && it[i].texId >= 0);
 	uint32_t maxFramePrims = 0;
 	for (uint32_t s2 = 0; s2 < numActive; s2++) maxFramePrims = std::max(maxFramePrims, fs[s2].primEnd - fs[s2].primBegin);
 	rc = run_pipeline(c, numActive, numItems, (uint32_t)prim, maxFramePrims, false);

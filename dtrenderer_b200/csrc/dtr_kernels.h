@@ -77,6 +77,7 @@ struct RasterParams
 	unsigned long long *setPixels;
 	uint32_t           *workCounter;    // zeroed by scan_kernel; items handed out by atomicAdd
 	const uint32_t     *numBusy;        // written by scan_kernel
+	uint32_t            anyTextured;    // some primitive of this pass samples a texture: raster_tex_kernel
 	uint32_t            numTiles;       // filled by launch_raster
 	uint32_t            smallTilesMin;  // filled by launch_raster: busy tiles rasterised as fine-grained items
 	Geometry            g;
