@@ -227,6 +227,26 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-rank runs: keep this rank's host threads -- and with them the pinned readback buffers it
+    allocates next -- on the CPUs closest to its GPU (NVML's ideal affinity), so that eight ranks'
+    D2H streams do not all land on one socket's memory.  Best effort; a no-op if NVML says nothing."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def run_gpu_arm(args, rank, world, local_rank):
     w, h, textured, tex_size, desc = WORKLOADS[args.workload]
     B = args.views
@@ -243,6 +263,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device -- this back end has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        bind_to_gpu_numa_node(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
