@@ -106,7 +106,7 @@ struct dtr_b200_ctx
 	// kernel of replay i is still finishing on the main stream.
 	struct PipeSet
 	{
-		DevBuf              prims, bounds, tileCount, tileOffset, order, lists, segRel;
+		DevBuf              prims, bounds, tileCount, tileOffset, order, lists, listBounds, segRel;
 		unsigned long long *counters = nullptr; // [1] list total, [3] work counter, [4] busy tiles
 		cudaEvent_t         preDone = nullptr, rasterDone = nullptr;
 		bool                rasterPending = false; // rasterDone has been recorded: the set may still be read
@@ -376,6 +376,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 		if (total >= (1ull << 31)) return fail(c, DTR_B200_ERR_OVERFLOW, "more than 2^31 (primitive, tile) pairs in one flush");
 	}
 	if ((rc = ensure_dev(c, S.lists, sizeof(uint32_t) * (size_t)std::max<uint64_t>(total, 1)))) return rc;
+	if ((rc = ensure_dev(c, S.listBounds, 2 * sizeof(uint32_t) * (size_t)std::max<uint64_t>(total, 1)))) return rc;
 
 	if (numPrims && total)
 	{
@@ -386,7 +387,8 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 		B.segRel       = (const uint32_t *)S.segRel.p;
 		B.tileOffset   = (const uint32_t *)S.tileOffset.p;
 		B.lists        = (uint32_t *)S.lists.p;
-		B.listCapacity = (uint32_t)(S.lists.cap / sizeof(uint32_t));
+		B.listBounds   = (uint2 *)S.listBounds.p;
+		B.listCapacity = (uint32_t)std::min(S.lists.cap / sizeof(uint32_t), S.listBounds.cap / (2 * sizeof(uint32_t)));
 		B.groupRows    = 0;
 		B.g            = g;
 		launch_bin(B, pre);
@@ -409,6 +411,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	R.tileOffset = (const uint32_t *)S.tileOffset.p;
 	R.order      = (const uint32_t *)S.order.p;
 	R.lists      = (const uint32_t *)S.lists.p;
+	R.listBounds = (const uint2 *)S.listBounds.p;
 	R.textures   = (const TexDesc *)c->dTextures.p;
 	R.setPixels  = c->dSetPixels;
 	R.workCounter    = (uint32_t *)(S.counters + 3);
@@ -631,7 +634,7 @@ void dtr_b200_destroy(dtr_b200_ctx *c)
 	std::vector<DevBuf *> bufs = {&c->dTextures, &c->dCmd, &c->dPayload};
 	for (auto &ps : c->sets)
 	{
-		for (DevBuf *b : {&ps.prims, &ps.bounds, &ps.tileCount, &ps.tileOffset, &ps.order, &ps.lists, &ps.segRel}) bufs.push_back(b);
+		for (DevBuf *b : {&ps.prims, &ps.bounds, &ps.tileCount, &ps.tileOffset, &ps.order, &ps.lists, &ps.listBounds, &ps.segRel}) bufs.push_back(b);
 		cudaFree(ps.counters);
 		if (ps.preDone) cudaEventDestroy(ps.preDone);
 		if (ps.rasterDone) cudaEventDestroy(ps.rasterDone);

@@ -57,6 +57,7 @@ struct BinParams
 	const uint32_t   *segRel;     // [numTiles * segs] offset of a segment's entries inside its tile list (segs > 1)
 	const uint32_t   *tileOffset; // [numTiles + 1]
 	uint32_t         *lists;
+	uint2            *listBounds; // [listCapacity] bbox of every list entry, same positions
 	uint32_t          listCapacity;
 	int32_t           groupRows; // tile rows per CTA, filled by launch_bin
 	Geometry          g;
@@ -73,6 +74,7 @@ struct RasterParams
 	const uint32_t     *tileOffset;
 	const uint32_t     *order; // work order written by scan_kernel
 	const uint32_t     *lists;
+	const uint2        *listBounds;
 	const TexDesc      *textures;
 	unsigned long long *setPixels;
 	uint32_t           *workCounter;    // zeroed by scan_kernel; items handed out by atomicAdd
