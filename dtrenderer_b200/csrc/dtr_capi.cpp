@@ -314,7 +314,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	const size_t countWords  = (numSeg + tileWords + 1) & ~(size_t)1; // keep the 64-bit words aligned
 	const size_t statusWords = scan_status_words(numTiles);
 	if ((rc = ensure_dev(c, S.tileCount, sizeof(uint32_t) * countWords + sizeof(unsigned long long) * statusWords))) return rc;
-	if ((rc = ensure_dev(c, S.order, sizeof(uint32_t) * std::max<size_t>(numTiles, 1)))) return rc;
+	if ((rc = ensure_dev(c, S.order, 32 * std::max<size_t>(numTiles, 1)))) return rc;
 	if ((rc = ensure_dev(c, S.tileOffset, sizeof(uint32_t) * ((size_t)numTiles + 1)))) return rc;
 	if ((rc = ensure_dev(c, S.segRel, sizeof(uint32_t) * std::max<size_t>(g.segs > 1 ? numSeg : 1, 1)))) return rc;
 	if ((rc = ensure_dev(c, S.prims, sizeof(PrimRecord) * (size_t)std::max(numPrims, 1u)))) return rc;
@@ -357,7 +357,9 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	SC.counts      = dTileCount;
 	SC.offsets     = (uint32_t *)S.tileOffset.p;
 	SC.n           = numTiles;
-	SC.order       = (uint32_t *)S.order.p;
+	SC.order       = (uint4 *)S.order.p;
+	SC.frames      = dFrames;
+	SC.bandTiles   = (uint32_t)g.bandTiles;
 	SC.status      = dScanStatus;
 	SC.totals      = S.counters + 1;
 	SC.workCounter = (uint32_t *)(S.counters + 3);
@@ -409,7 +411,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	R.bounds     = (const PrimBounds *)S.bounds.p;
 	R.tileCount  = dTileCount;
 	R.tileOffset = (const uint32_t *)S.tileOffset.p;
-	R.order      = (const uint32_t *)S.order.p;
+	R.order      = (const uint4 *)S.order.p;
 	R.lists      = (const uint32_t *)S.lists.p;
 	R.listBounds = (const uint2 *)S.listBounds.p;
 	R.textures   = (const TexDesc *)c->dTextures.p;

@@ -31,7 +31,10 @@ struct ScanParams
 	const uint32_t     *counts;   // per-tile counts [n]
 	uint32_t           *offsets;  // [n + 1]
 	uint32_t            n;
-	uint32_t           *order;    // [n] raster work order: busy tiles first, untouched tiles last
+	uint4              *order;    // [2n] raster work order (busy tiles first, untouched last), 32 bytes per tile:
+	                              // {tile, list length, list offset, plane index} {clear colour, init flags, -, -}
+	const FrameState   *frames;
+	uint32_t            bandTiles;
 	unsigned long long *status;   // [chunks] look-back words, zeroed before the launch
 	unsigned long long *totals;   // [0] list total
 	uint32_t           *workCounter;
@@ -72,7 +75,7 @@ struct RasterParams
 	const PrimBounds   *bounds;
 	const uint32_t     *tileCount;
 	const uint32_t     *tileOffset;
-	const uint32_t     *order; // work order written by scan_kernel
+	const uint4        *order; // work order + tile descriptors written by scan_kernel
 	const uint32_t     *lists;
 	const uint2        *listBounds;
 	const TexDesc      *textures;
