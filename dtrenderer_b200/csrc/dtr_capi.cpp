@@ -110,6 +110,7 @@ struct dtr_b200_ctx
 		unsigned long long *counters = nullptr; // [1] list total, [3] work counter, [4] busy tiles
 		cudaEvent_t         preDone = nullptr, rasterDone = nullptr;
 		bool                rasterPending = false; // rasterDone has been recorded: the set may still be read
+		size_t              cleanBytes = 0;        // the first cleanBytes of tileCount were zeroed by the last raster kernel
 	};
 	PipeSet             sets[2];
 	int                 nextReplaySet = 1;
@@ -313,7 +314,11 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	const size_t tileWords   = g.segs > 1 ? (size_t)numTiles : 0;
 	const size_t countWords  = (numSeg + tileWords + 1) & ~(size_t)1; // keep the 64-bit words aligned
 	const size_t statusWords = scan_status_words(numTiles);
-	if ((rc = ensure_dev(c, S.tileCount, sizeof(uint32_t) * countWords + sizeof(unsigned long long) * statusWords))) return rc;
+	{
+		const void *before = S.tileCount.p;
+		if ((rc = ensure_dev(c, S.tileCount, sizeof(uint32_t) * countWords + sizeof(unsigned long long) * statusWords))) return rc;
+		if (S.tileCount.p != before) S.cleanBytes = 0; // a new allocation has not been cleared by anyone
+	}
 	if ((rc = ensure_dev(c, S.order, 32 * std::max<size_t>(numTiles, 1)))) return rc;
 	if ((rc = ensure_dev(c, S.tileOffset, sizeof(uint32_t) * ((size_t)numTiles + 1)))) return rc;
 	if ((rc = ensure_dev(c, S.segRel, sizeof(uint32_t) * std::max<size_t>(g.segs > 1 ? numSeg : 1, 1)))) return rc;
@@ -324,7 +329,10 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 
 	unsigned long long *dScanStatus = (unsigned long long *)(dSegCount + countWords);
 	if ((rc = mark(c, pre))) return rc;
-	CU(cudaMemsetAsync(dSegCount, 0, sizeof(uint32_t) * countWords + sizeof(unsigned long long) * statusWords, pre));
+	const size_t zeroBytes = sizeof(uint32_t) * countWords + sizeof(unsigned long long) * statusWords;
+	// a replay finds the counters already cleared by the previous raster kernel of this set
+	if (!(replay && S.cleanBytes >= zeroBytes)) CU(cudaMemsetAsync(dSegCount, 0, zeroBytes, pre));
+	S.cleanBytes = 0;
 	if (numPrims)
 	{
 		SetupParams SP;
@@ -418,6 +426,8 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	R.setPixels  = c->dSetPixels;
 	R.workCounter    = (uint32_t *)(S.counters + 3);
 	R.numBusy        = (const uint32_t *)(S.counters + 4);
+	R.zeroBase       = dSegCount;
+	R.zeroWords      = zeroBytes / sizeof(uint32_t);
 	R.anyTextured    = c->last.anyTextured ? 1u : 0u;
 	R.numTiles       = 0;
 	R.smallTilesMin  = 0;
@@ -428,6 +438,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	if ((rc = mark(c, c->stream))) return rc;
 	CU(cudaEventRecord(S.rasterDone, c->stream));
 	S.rasterPending = true;
+	S.cleanBytes    = zeroBytes;
 	CU(cudaGetLastError());
 
 	c->last.valid     = true;

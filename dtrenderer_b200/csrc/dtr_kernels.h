@@ -7,7 +7,7 @@
 namespace dtr
 {
 
-constexpr int SETUP_THREADS = 128;
+constexpr int SETUP_THREADS = 64; // 64 x 56 registers fit next to five resident raster CTAs: setup of the next replay runs DURING the raster kernel
 
 struct SetupParams
 {
@@ -23,7 +23,7 @@ struct SetupParams
 	Geometry        g;
 };
 
-constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_THREADS = 64;    // small CTAs (64 x 32 registers) fit next to five resident raster CTAs
 constexpr int SCAN_CHUNK   = SCAN_THREADS * 4; // counts scanned per CTA
 
 struct ScanParams
@@ -82,6 +82,8 @@ struct RasterParams
 	unsigned long long *setPixels;
 	uint32_t           *workCounter;    // zeroed by scan_kernel; items handed out by atomicAdd
 	const uint32_t     *numBusy;        // written by scan_kernel
+	uint32_t           *zeroBase;       // counters + look-back words to clear for the next pass (may be null)
+	size_t              zeroWords;
 	uint32_t            anyTextured;    // some primitive of this pass samples a texture: raster_tex_kernel
 	uint32_t            numTiles;       // filled by launch_raster
 	uint32_t            smallTilesMin;  // filled by launch_raster: busy tiles rasterised as fine-grained items
