@@ -7,7 +7,7 @@
 namespace dtr
 {
 
-constexpr int SETUP_THREADS = 64; // 64 x 56 registers fit next to five resident raster CTAs: setup of the next replay runs DURING the raster kernel
+constexpr int SETUP_THREADS = 64; // 64 x 48 registers fit next to five resident raster CTAs: setup of the next replay runs DURING the raster kernel
 
 struct SetupParams
 {
