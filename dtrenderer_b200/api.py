@@ -66,6 +66,7 @@ SYMBOLS = [
     ("dtr_b200_read_frames", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     ("dtr_b200_read_frames_async", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     ("dtr_b200_wait_reads", C.c_int, [C.c_void_p]),
+    ("dtr_b200_read_frames_bgr24_async", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     ("dtr_b200_export_frames", C.c_int, [C.c_void_p, _u8, _u8]),
     ("dtr_b200_open_peer_frames", C.c_int, [C.c_void_p, _u8, _u8]),
     ("dtr_b200_set_output_planes", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -252,6 +253,15 @@ class Renderer:
         returns at once.  wait_reads() blocks until every outstanding readback has landed."""
         self._ck(self.lib.dtr_b200_read_frames_async(self.ctx, first, n, C.c_void_p(color_ptr),
                                                      C.c_void_p(z_ptr) if z_ptr else None))
+
+    def bgr24_pitch(self):
+        """Row pitch in bytes of the 24-bit DIB rows written by read_frames_bgr24_async_ptr."""
+        return (3 * self.width + 3) & ~3
+
+    def read_frames_bgr24_async_ptr(self, first, n, bgr_ptr):
+        """Flush, pack n colour planes into 24-bit bottom-up DIBs on the device and enqueue their
+        readback (n * bgr24_pitch() * height bytes of page-locked memory); wait_reads() completes it."""
+        self._ck(self.lib.dtr_b200_read_frames_bgr24_async(self.ctx, first, n, C.c_void_p(bgr_ptr)))
 
     def wait_reads(self):
         self._ck(self.lib.dtr_b200_wait_reads(self.ctx))

@@ -69,6 +69,11 @@ struct dtr_b200_ctx
 	// by renderDone; copyDone lets a later flush that renders into frames still being read wait
 	cudaStream_t copyStream = nullptr;
 	cudaEvent_t  renderDone = nullptr, copyDone = nullptr;
+	// 24-bit presentation readback (dtr_b200_read_frames_bgr24_async): two device staging buffers
+	// used in turn, so that packing the next batch does not wait for the previous transfer
+	DevBuf       packStage[2];
+	cudaEvent_t  packFree[2] = {nullptr, nullptr}; // the D2H copy out of packStage[k] has finished
+	int          packTurn    = 0;
 	int          readLo = 0, readHi = 0; // frames [readLo, readHi) have reads in flight
 	struct FontHost
 	{
@@ -669,6 +674,11 @@ void dtr_b200_destroy(dtr_b200_ctx *c)
 	}
 	if (c->renderDone) cudaEventDestroy(c->renderDone);
 	if (c->copyDone) cudaEventDestroy(c->copyDone);
+	for (int k = 0; k < 2; k++)
+	{
+		cudaFree(c->packStage[k].p);
+		if (c->packFree[k]) cudaEventDestroy(c->packFree[k]);
+	}
 	if (c->preStream) cudaStreamDestroy(c->preStream);
 	if (c->ownStream) cudaStreamDestroy(c->ownStream);
 	delete c;
@@ -904,6 +914,36 @@ int dtr_b200_read_frames_async(dtr_b200_ctx *c, int first, int n, uint32_t *host
 		c->readLo = first;
 		c->readHi = first + n;
 	}
+	return DTR_B200_OK;
+}
+
+int dtr_b200_read_frames_bgr24_async(dtr_b200_ctx *c, int first, int n, uint8_t *hostBgr)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (n <= 0 || !hostBgr || !valid_frame(c, first) || !valid_frame(c, first + n - 1))
+		return fail(c, DTR_B200_ERR_ARG, "frame range out of bounds or NULL destination");
+	CU(cudaSetDevice(c->device));
+	int rc = do_flush(c);
+	if (rc) return rc;
+	const size_t pitch = ((size_t)c->width * 3 + 3) & ~(size_t)3, rows = (size_t)n * c->height, bytes = pitch * rows;
+	const int    k     = c->packTurn;
+	c->packTurn ^= 1;
+	if (!c->packFree[k]) CU(cudaEventCreateWithFlags(&c->packFree[k], cudaEventDisableTiming));
+	else CU(cudaStreamWaitEvent(c->stream, c->packFree[k], 0)); // the previous transfer out of this buffer
+	if (bytes > c->packStage[k].cap)
+	{
+		CU(cudaStreamSynchronize(c->copyStream)); // ensure_dev frees the old buffer
+		rc = ensure_dev(c, c->packStage[k], bytes);
+		if (rc) return rc;
+	}
+	// the frames are free again as soon as the pack kernel has run (same stream as the rendering)
+	launch_pack_bgr24(c->outColor + (size_t)c->width * c->height * first, static_cast<uint32_t *>(c->packStage[k].p), c->width, rows,
+	                  (int)(pitch / 4), c->stream);
+	CU(cudaGetLastError());
+	CU(cudaEventRecord(c->renderDone, c->stream));
+	CU(cudaStreamWaitEvent(c->copyStream, c->renderDone, 0));
+	CU(cudaMemcpyAsync(hostBgr, c->packStage[k].p, bytes, cudaMemcpyDeviceToHost, c->copyStream));
+	CU(cudaEventRecord(c->packFree[k], c->copyStream));
 	return DTR_B200_OK;
 }
 

@@ -99,5 +99,6 @@ void launch_selftest_sqrt(unsigned long long *mismatches, cudaStream_t s);
 void launch_bin(const BinParams &P, cudaStream_t s);
 void launch_raster(const RasterParams &P, cudaStream_t s);
 void launch_premultiply(uint32_t *pixels, size_t count, cudaStream_t s);
+void launch_pack_bgr24(const uint32_t *color, uint32_t *out, int width, size_t rows, int pitchWords, cudaStream_t s);
 
 } // namespace dtr

@@ -158,6 +158,14 @@ int dtr_b200_read_frames(dtr_b200_ctx *ctx, int firstFrame, int n, uint32_t *hos
  * buffers must be page-locked for the copy to overlap; they are valid after dtr_b200_wait_reads. */
 int dtr_b200_read_frames_async(dtr_b200_ctx *ctx, int firstFrame, int n, uint32_t *hostColor, float *hostZ);
 int dtr_b200_wait_reads(dtr_b200_ctx *ctx);
+/* The same hand-off with an on-device encode ("on-device encode"): the X
+ * byte of DTRRenderBuffer's 0x00RRGGBB pixels (DTRendererRender.h:14-25) is always 0, so the n
+ * colour planes are packed on the device into 24-bit bottom-up DIBs -- B,G,R per pixel, row pitch
+ * ((3*W + 3) & ~3) bytes, rows bottom first like the planes -- which StretchDIBits
+ * (Win32DTRenderer.cpp:267-284) presents with biBitCount = 24, and 3/4 of the bytes cross PCIe.
+ * hostBgr: n * pitch * H bytes, page-locked; valid after dtr_b200_wait_reads.  The frames may be
+ * rendered into again at once (the pack runs in stream order, the transfer reads a staging copy). */
+int dtr_b200_read_frames_bgr24_async(dtr_b200_ctx *ctx, int firstFrame, int n, uint8_t *hostBgr);
 /* Sort-first screen bands WITHOUT a gather step: every rank rasterises its band
  * (dtr_b200_set_band) but writes the finished regions straight into the gathering rank's frame
  * planes over NVLink, from inside the raster kernel's write-back -- the transfer overlaps the

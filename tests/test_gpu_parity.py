@@ -329,6 +329,38 @@ def test_async_readback_double_buffered(built):
     _assert_same(col, z, o.color(), o.zbuffer())
 
 
+@pytest.mark.parametrize("size", [(320, 200), (333, 217), (5, 3)])
+def test_bgr24_presentation_readback(built, size):
+    """On-device 24-bit DIB encode: every row is the B,G,R bytes of the oracle's
+    0x00RRGGBB pixels, padded to 4 bytes with zeros; three reads in a row alternate the staging
+    buffers while the frames are re-rendered in between."""
+    import torch
+    w, h = size
+    n = 3
+    r = _renderer(w, h, n)
+    pitch = r.bgr24_pitch()
+    assert pitch == (3 * w + 3) // 4 * 4
+    mesh, tex = scenes.uv_sphere(12, 6), scenes.random_texture(16, 16, 5, True)
+    ts = scenes.view_transforms(4096)[100:100 + n]
+    host = torch.full((3, n, h, pitch), 0xAB, dtype=torch.uint8, pin_memory=True)
+    clears = [(0.5, 0.0, 1.0), (0.1, 0.9, 0.2), (1.0, 1.0, 1.0)]
+    for k, clear in enumerate(clears):
+        for f in range(n):
+            r.begin_frame(f)
+            r.clear(clear)
+        r.mesh_views(mesh, tex, scenes.SHADE_GOURAUD, (1, -1, 1), (1, 1, 1, 1), np.zeros((n, 3), np.float32), ts, 0)
+        r.read_frames_bgr24_async_ptr(0, n, host[k].data_ptr())
+    r.wait_reads()
+    for k, clear in enumerate(clears):
+        for f in range(n):
+            o = _oracle(w, h)
+            o.clear(clear)
+            o.mesh(mesh, tex, scenes.SHADE_GOURAUD, (1, -1, 1), (1, 1, 1, 1), (0, 0, 0), ts[f])
+            want = np.zeros((h, pitch), np.uint8)
+            want[:, :3 * w] = o.color().view(np.uint8).reshape(h, w, 4)[:, :, :3].reshape(h, 3 * w)
+            assert np.array_equal(host[k, f].numpy(), want)
+
+
 def test_tiny_translucent_overlaps_keep_submission_order(built):
     """Thousands of 1-20 pixel triangles, half of them translucent, piled on a small area: fragments
     of many triangles share one shading batch, and the same pixel occurs several times in a batch.
