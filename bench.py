@@ -340,27 +340,37 @@ def run_gpu_arm(args, rank, world, local_rank):
     host = torch.empty((2, B, h, w), dtype=torch.int32, pin_memory=True)
     e2e_steps = max(2, min(args.steps, args.e2e_steps))
 
-    def step_e2e(i):
-        half = i & 1
-        record(half * B)
-        r.read_frames_async_ptr(half * B, B, host[half].data_ptr())
+    def time_e2e(read_half):
+        def step_e2e(i):
+            half = i & 1
+            record(half * B)
+            read_half(half)
 
-    for i in range(2):
-        step_e2e(i)
-    r.wait_reads()
-    barrier()
-    clocks.start()
-    e0.record(stream)
-    for i in range(e2e_steps):
-        step_e2e(i)
-    r.wait_reads()  # blocks until the last copy has landed; e1 is recorded after that
-    e1.record(stream)
-    barrier()
-    clocks.pause()
-    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item()) / e2e_steps
+        for i in range(2):
+            step_e2e(i)
+        r.wait_reads()
+        barrier()
+        clocks.start()
+        e0.record(stream)
+        for i in range(e2e_steps):
+            step_e2e(i)
+        r.wait_reads()  # blocks until the last copy has landed; e1 is recorded after that
+        e1.record(stream)
+        barrier()
+        clocks.pause()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / e2e_steps
+
+    e2e_ms = time_e2e(lambda half: r.read_frames_async_ptr(half * B, B, host[half].data_ptr()))
+    # the same loop with the on-device 24-bit DIB encode (3 bytes per pixel over PCIe); reported beside
+    # `e2e`, which stays the u32 DTRRenderBuffer layout
+    pitch = r.bgr24_pitch()
+    host24 = torch.empty((2, B, h, pitch), dtype=torch.uint8, pin_memory=True)
+    e2e24_ms = time_e2e(lambda half: r.read_frames_bgr24_async_ptr(half * B, B, host24[half].data_ptr()))
+    packed_ok = bool(torch.equal(host24[1, :, :, :3 * w].reshape(B, h, w, 3),
+                                 host[1].view(torch.uint8).reshape(B, h, w, 4)[..., :3]))
     checksum = int(host[0, 0].view(-1)[::997].to(torch.int64).sum().item())
 
     if rank == 0:
@@ -396,6 +406,11 @@ def run_gpu_arm(args, rank, world, local_rank):
                     "readback": "colour planes only (what the reference presents); depth stays in HBM; "
                                 "asynchronous and double buffered (step i's D2H overlaps step i+1's rendering)",
                     "checksum": checksum},
+            "e2e_bgr24": {"value": world * shaded_per_step / (e2e24_ms * 1e-3) / 1e9, "unit": UNIT,
+                          "d2h_bytes_per_step": B * pitch * h, "ms_per_step": e2e24_ms,
+                          "matches_u32_readback": packed_ok,
+                          "readback": "dtr_b200_read_frames_bgr24_async: colour packed on the device into 24-bit "
+                                      "bottom-up DIB rows (informational; `e2e` is the DTRRenderBuffer layout)"},
             "gpu_launches": launches, "clocks": clocks.result(),
         }
         print(json.dumps(line), flush=True)
