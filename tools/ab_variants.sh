@@ -1,3 +1,5 @@
+# A/B of kernel variants on the GPU box: build variants/libdtr_<name>.so (same sources, other -D flags), then
+# `gpurun -- bash tools/ab_variants.sh <name>...`; the library under test is selected with DTR_B200_LIB.
 cd /root/repo
 run() { # name lib
   for w in mesh1080 fill4k; do
