@@ -29,6 +29,10 @@ namespace
 
 std::string g_createError;
 
+#ifndef DTR_PIPE_SETS
+#define DTR_PIPE_SETS 3
+#endif
+
 struct DevBuf
 {
 	void  *p   = nullptr;
@@ -106,9 +110,13 @@ struct dtr_b200_ctx
 	DevBuf                 dTextures;
 
 	DevBuf dCmd, dPayload;
-	// Intermediate buffers of one pass of the pipeline.  Two sets: a flush uses set 0; replays
-	// alternate, so that setup / scan / bin of replay i+1 (on preStream) can run while the raster
-	// kernel of replay i is still finishing on the main stream.
+	// Intermediate buffers of one pass of the pipeline.  PIPE_SETS sets: a flush uses set 0; replays
+	// take them in turn, so that setup / scan / bin of a later replay (on preStream) run while the
+	// raster kernels of earlier replays occupy the main stream.  With THREE sets the pre-raster stages
+	// run two replays ahead: setup and scan of replay i+2 (small CTAs) co-run with raster i, bin i+2
+	// takes the SM slots that free up at the end of raster i and runs beside the START of raster i+1,
+	// which depends only on bin i+1 (long finished) and therefore launches back to back with raster i.
+	// (With two sets raster i+1 had to wait for bin i+1, which could not start before raster i ended.)
 	struct PipeSet
 	{
 		DevBuf              prims, bounds, tileCount, tileOffset, order, lists, listBounds, segRel;
@@ -117,7 +125,8 @@ struct dtr_b200_ctx
 		bool                rasterPending = false; // rasterDone has been recorded: the set may still be read
 		size_t              cleanBytes = 0;        // the first cleanBytes of tileCount were zeroed by the last raster kernel
 	};
-	PipeSet             sets[2];
+	static constexpr int PIPE_SETS = DTR_PIPE_SETS;
+	PipeSet             sets[PIPE_SETS];
 	int                 nextReplaySet = 1;
 	bool                replayOverlap = true; // dtr_b200_set_replay_overlap
 	cudaStream_t        preStream = nullptr;
@@ -310,7 +319,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	const bool             overlap = replay && c->replayOverlap;
 	dtr_b200_ctx::PipeSet &S   = c->sets[overlap ? c->nextReplaySet : 0];
 	const cudaStream_t     pre = overlap ? c->preStream : c->stream;
-	if (overlap) c->nextReplaySet ^= 1;
+	if (overlap) c->nextReplaySet = (c->nextReplaySet + 1) % dtr_b200_ctx::PIPE_SETS;
 	else if (replay) CU(cudaStreamSynchronize(c->preStream)); // set 0 may be in use by an overlapped replay
 	if (S.rasterPending && pre != c->stream) CU(cudaStreamWaitEvent(pre, S.rasterDone, 0));
 
