@@ -382,6 +382,8 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	SC.order       = (uint4 *)S.order.p;
 	SC.frames      = dFrames;
 	SC.bandTiles   = (uint32_t)g.bandTiles;
+	SC.tilesX      = (uint32_t)g.tilesX;
+	SC.bandTileY0  = (uint32_t)g.bandTileY0;
 	SC.status      = dScanStatus;
 	SC.totals      = S.counters + 1;
 	SC.workCounter = (uint32_t *)(S.counters + 3);

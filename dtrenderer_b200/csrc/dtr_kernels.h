@@ -32,9 +32,9 @@ struct ScanParams
 	uint32_t           *offsets;  // [n + 1]
 	uint32_t            n;
 	uint4              *order;    // [2n] raster work order (busy tiles first, untouched last), 32 bytes per tile:
-	                              // {tile, list length, list offset, plane index} {clear colour, init flags, -, -}
+	                              // {tile, list length, list offset, plane index} {clear colour, init flags, tx | ty << 16, -}
 	const FrameState   *frames;
-	uint32_t            bandTiles;
+	uint32_t            bandTiles, tilesX, bandTileY0;
 	unsigned long long *status;   // [chunks] look-back words, zeroed before the launch
 	unsigned long long *totals;   // [0] list total
 	uint32_t           *workCounter;
