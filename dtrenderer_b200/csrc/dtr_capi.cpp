@@ -119,7 +119,7 @@ struct dtr_b200_ctx
 	// (With two sets raster i+1 had to wait for bin i+1, which could not start before raster i ended.)
 	struct PipeSet
 	{
-		DevBuf              prims, bounds, tileCount, tileOffset, order, lists, listBounds, segRel;
+		DevBuf              prims, bounds, primZ, tileCount, tileOffset, order, lists, listBounds, listZ, segRel;
 		unsigned long long *counters = nullptr; // [1] list total, [3] work counter, [4] busy tiles
 		cudaEvent_t         preDone = nullptr, rasterDone = nullptr;
 		bool                rasterPending = false; // rasterDone has been recorded: the set may still be read
@@ -338,6 +338,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	if ((rc = ensure_dev(c, S.segRel, sizeof(uint32_t) * std::max<size_t>(g.segs > 1 ? numSeg : 1, 1)))) return rc;
 	if ((rc = ensure_dev(c, S.prims, sizeof(PrimRecord) * (size_t)std::max(numPrims, 1u)))) return rc;
 	if ((rc = ensure_dev(c, S.bounds, sizeof(PrimBounds) * (size_t)std::max(numPrims, 1u)))) return rc;
+	if ((rc = ensure_dev(c, S.primZ, sizeof(int32_t) * (size_t)std::max(numPrims, 1u)))) return rc;
 	uint32_t *dSegCount  = (uint32_t *)S.tileCount.p;
 	uint32_t *dTileCount = g.segs > 1 ? dSegCount + numSeg : dSegCount; // with one segment they are the same thing
 
@@ -356,6 +357,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 		SP.numPrims    = numPrims;
 		SP.prims       = (PrimRecord *)S.prims.p;
 		SP.bounds      = (PrimBounds *)S.bounds.p;
+		SP.primZ       = (int32_t *)S.primZ.p;
 		SP.segCount    = dSegCount;
 		SP.frames      = dFrames;
 		SP.textures    = (const TexDesc *)c->dTextures.p;
@@ -403,6 +405,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	}
 	if ((rc = ensure_dev(c, S.lists, sizeof(uint32_t) * (size_t)std::max<uint64_t>(total, 1)))) return rc;
 	if ((rc = ensure_dev(c, S.listBounds, 2 * sizeof(uint32_t) * (size_t)std::max<uint64_t>(total, 1)))) return rc;
+	if ((rc = ensure_dev(c, S.listZ, sizeof(int32_t) * (size_t)std::max<uint64_t>(total, 1)))) return rc;
 
 	if (numPrims && total)
 	{
@@ -414,7 +417,9 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 		B.tileOffset   = (const uint32_t *)S.tileOffset.p;
 		B.lists        = (uint32_t *)S.lists.p;
 		B.listBounds   = (uint2 *)S.listBounds.p;
-		B.listCapacity = (uint32_t)std::min(S.lists.cap / sizeof(uint32_t), S.listBounds.cap / (2 * sizeof(uint32_t)));
+		B.primZ        = (const int32_t *)S.primZ.p;
+		B.listZ        = (int32_t *)S.listZ.p;
+		B.listCapacity = (uint32_t)std::min({S.lists.cap / sizeof(uint32_t), S.listBounds.cap / (2 * sizeof(uint32_t)), S.listZ.cap / sizeof(int32_t)});
 		B.groupRows    = 0;
 		B.g            = g;
 		launch_bin(B, pre);
@@ -438,6 +443,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	R.order      = (const uint4 *)S.order.p;
 	R.lists      = (const uint32_t *)S.lists.p;
 	R.listBounds = (const uint2 *)S.listBounds.p;
+	R.listZ      = (const int32_t *)S.listZ.p;
 	R.textures   = (const TexDesc *)c->dTextures.p;
 	R.setPixels  = c->dSetPixels;
 	R.workCounter    = (uint32_t *)(S.counters + 3);
@@ -663,7 +669,7 @@ void dtr_b200_destroy(dtr_b200_ctx *c)
 	std::vector<DevBuf *> bufs = {&c->dTextures, &c->dCmd, &c->dPayload};
 	for (auto &ps : c->sets)
 	{
-		for (DevBuf *b : {&ps.prims, &ps.bounds, &ps.tileCount, &ps.tileOffset, &ps.order, &ps.lists, &ps.listBounds, &ps.segRel}) bufs.push_back(b);
+		for (DevBuf *b : {&ps.prims, &ps.bounds, &ps.primZ, &ps.tileCount, &ps.tileOffset, &ps.order, &ps.lists, &ps.listBounds, &ps.listZ, &ps.segRel}) bufs.push_back(b);
 		cudaFree(ps.counters);
 		if (ps.preDone) cudaEventDestroy(ps.preDone);
 		if (ps.rasterDone) cudaEventDestroy(ps.rasterDone);

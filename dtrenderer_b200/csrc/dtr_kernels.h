@@ -17,6 +17,7 @@ struct SetupParams
 	uint32_t        numPrims;
 	PrimRecord     *prims;
 	PrimBounds     *bounds;
+	int32_t        *primZ;     // per primitive: depth_key of an upper bound of its depths (INT_MAX: unknown / not a depth-tested triangle)
 	uint32_t       *segCount;  // [numFrames * bandTiles * segs] primitives per (tile, segment); == tile counts when segs == 1
 	const FrameState *frames;
 	const TexDesc  *textures; // texture table: pointer and size are copied into textured records
@@ -61,6 +62,8 @@ struct BinParams
 	const uint32_t   *tileOffset; // [numTiles + 1]
 	uint32_t         *lists;
 	uint2            *listBounds; // [listCapacity] bbox of every list entry, same positions
+	const int32_t    *primZ;      // per primitive depth bound (see SetupParams)
+	int32_t          *listZ;      // [listCapacity] ... and its depth bound
 	uint32_t          listCapacity;
 	int32_t           groupRows; // tile rows per CTA, filled by launch_bin
 	Geometry          g;
@@ -78,6 +81,7 @@ struct RasterParams
 	const uint4        *order; // work order + tile descriptors written by scan_kernel
 	const uint32_t     *lists;
 	const uint2        *listBounds;
+	const int32_t      *listZ;
 	const TexDesc      *textures;
 	unsigned long long *setPixels;
 	uint32_t           *workCounter;    // zeroed by scan_kernel; items handed out by atomicAdd
