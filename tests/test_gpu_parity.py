@@ -86,6 +86,52 @@ def test_random_transformed_triangles(built):
     _assert_same(col, z, o.color(), o.zbuffer())
 
 
+def test_depth_cull_behind_occluders(built):
+    """Region-level depth cull: occluders laid down first (full-frame and partial, flat and slanted,
+    one pair translucent -- it still writes depth), then thousands of integer-vertex triangles whose
+    depths straddle them: behind, in front, crossing, and EXACTLY on the occluder's plane (strict `>`
+    must reject those, and a later triangle one ulp nearer must still pass).  A later flush draws
+    into the kept depth buffer (the cull then starts from loaded depths)."""
+    rng = np.random.default_rng(99)
+    w, h = 320, 200
+    o, r = _oracle(w, h), _renderer(w, h)
+    o.reset_counters()
+    r.begin_frame(0)
+    both = (o, r)
+    for t in both:
+        t.clear((0.1, 0.2, 0.3))
+
+    def quad(x0, y0, x1, y1, zs, col):
+        a = np.array([[x0, y0, zs[0], x1, y0, zs[1], x1, y1, zs[2]], [x0, y0, zs[0], x1, y1, zs[2], x0, y1, zs[3]]], np.float32)
+        c = np.tile(np.asarray(col, np.float32), (2, 1))
+        for t in both:
+            t.triangles(a, c, scenes.DEFAULT_TRIANGLE_TRANSFORM)
+
+    quad(-5, -5, w + 5, h + 5, (100, 100, 100, 100), (0.9, 0.1, 0.1, 1.0))          # flat wall at z = 100
+    quad(40, 30, 200, 150, (60, 180, 220, 90), (0.1, 0.9, 0.1, 1.0))                # slanted, crosses the wall
+    quad(150, 20, 300, 120, (140, 140, 140, 140), (0.2, 0.2, 0.9, 0.5))             # translucent, writes depth
+    n = 4000
+    c = rng.integers(-10, [w + 10, h + 10], (n, 1, 2))
+    xy = c + rng.integers(-24, 25, (n, 3, 2))
+    z = rng.uniform(0, 255, (n, 3)).astype(np.float32)
+    kind = rng.integers(0, 6, n)
+    z[kind == 0] = 100.0                                                            # exactly on the wall: never passes
+    z[kind == 1] = np.nextafter(np.float32(100.0), np.float32(200.0))               # one ulp nearer: passes
+    z[kind == 2] = rng.uniform(0, 99, (int((kind == 2).sum()), 1)).astype(np.float32)  # flat, behind the wall
+    p = np.concatenate([xy, z[..., None]], 2).astype(np.float32).reshape(n, 9)
+    cols = rng.random((n, 4)).astype(np.float32)
+    cols[rng.random(n) < 0.7, 3] = 1.0
+    for k in range(4):
+        a, b = n * k // 4, n * (k + 1) // 4
+        for t in both:
+            t.triangles(p[a:b], cols[a:b], scenes.DEFAULT_TRIANGLE_TRANSFORM)
+        if k == 1:
+            r.flush()                                                               # the rest starts from depths kept in HBM
+    col, zb = r.end_frame(0)
+    _assert_same(col, zb, o.color(), o.zbuffer())
+    assert r.stats()["setPixels"] == o.counters()[0]
+
+
 def test_random_blits(built):
     """Rectangles and bilinear bitmaps with random rotation/scale/anchor, partly off-screen."""
     rng = np.random.default_rng(99)
