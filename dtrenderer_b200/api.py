@@ -37,6 +37,18 @@ class MeshDesc(C.Structure):
                 ("normals", _f), ("numNormals", C.c_uint32), ("faces", _i32), ("numFaces", C.c_uint32)]
 
 
+class MeshFace(C.Structure):
+    """dtr_b200_mesh_face == DTRMeshFace (DTRendererAsset.h:16-26): three host pointers + counts."""
+    _fields_ = [("vertexIndex", C.c_void_p), ("numVertexIndex", C.c_uint32), ("texIndex", C.c_void_p),
+                ("numTexIndex", C.c_uint32), ("normalIndex", C.c_void_p), ("numNormalIndex", C.c_uint32)]
+
+
+class MeshFacesDesc(C.Structure):
+    _fields_ = [("vertexes", _f), ("numVertexes", C.c_uint32), ("texUV", _f), ("numTexUV", C.c_uint32),
+                ("normals", _f), ("numNormals", C.c_uint32), ("faces", C.POINTER(MeshFace)), ("numFaces", C.c_uint32),
+                ("arena", C.c_void_p), ("arenaBytes", C.c_size_t)]
+
+
 class Stats(C.Structure):
     _fields_ = [("setPixels", C.c_uint64), ("triangles", C.c_uint64), ("primitives", C.c_uint64),
                 ("listEntries", C.c_uint64), ("kernelLaunches", C.c_uint64), ("uploadBytes", C.c_uint64)]
@@ -56,6 +68,15 @@ SYMBOLS = [
     ("dtr_b200_upload_bitmap_straight", C.c_int, [C.c_void_p, _u8, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     ("dtr_b200_read_texture", C.c_int, [C.c_void_p, C.c_int, _u8]),
     ("dtr_b200_upload_mesh", C.c_int, [C.c_void_p, C.POINTER(MeshDesc), C.c_int, C.POINTER(C.c_int)]),
+    ("dtr_b200_upload_mesh_faces", C.c_int, [C.c_void_p, C.POINTER(MeshFacesDesc), C.c_int, C.POINTER(C.c_int)]),
+    ("dtr_b200_update_texture", C.c_int, [C.c_void_p, C.c_int, _u8]),
+    ("dtr_b200_tile_height", C.c_int, []),
+    ("dtr_b200_band_rows", C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("dtr_b200_band_comm_unique_id", C.c_int, [_u8]),
+    ("dtr_b200_band_comm_init", C.c_int, [C.c_void_p, _u8, C.c_int, C.c_int]),
+    ("dtr_b200_band_comm_attach", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    ("dtr_b200_gather_bands", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("dtr_b200_band_barrier", C.c_int, [C.c_void_p]),
     ("dtr_b200_set_target", C.c_int, [C.c_void_p, C.c_int]),
     ("dtr_b200_begin_frame", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     ("dtr_b200_flush", C.c_int, [C.c_void_p]),
@@ -208,6 +229,65 @@ class Renderer:
         self._ck(self.lib.dtr_b200_upload_mesh(self.ctx, C.byref(d), tex_id, C.byref(mid)))
         self._mesh[key] = (mid.value, mesh)
         return mid.value
+
+    def upload_mesh_faces(self, mesh, faces, arena, tex_id):
+        """DTRMesh as the reference's loader leaves it: ``faces`` is a ctypes array of MeshFace whose
+        pointers lead into the numpy byte block ``arena``; the index table is flattened on the device."""
+        v, t, n = _fa(mesh["vertexes"]), _fa(mesh["texUV"]), _fa(mesh["normals"])
+        d = MeshFacesDesc(_fp(v), v.size // 4, _fp(t), t.size // 3, _fp(n), n.size // 3, faces, len(faces),
+                          C.c_void_p(arena.ctypes.data), arena.nbytes)
+        mid = C.c_int(-1)
+        self._ck(self.lib.dtr_b200_upload_mesh_faces(self.ctx, C.byref(d), tex_id, C.byref(mid)))
+        return mid.value
+
+    def update_texture(self, tex_id, tex):
+        """Re-upload a texture the host changed in place (same dimensions)."""
+        a = np.ascontiguousarray(tex, dtype=np.uint8)
+        self._ck(self.lib.dtr_b200_update_texture(self.ctx, tex_id, a.ctypes.data_as(_u8)))
+
+    def mesh_id(self, mesh_id, light_mode, light_vector, light_color, pos=(0, 0, 0), transform=None):
+        """DTRRender_Mesh with a mesh that is already on the device."""
+        light = self._light(light_mode, light_vector, light_color)
+        t = make_transform(transform)
+        self._ck(self.lib.dtr_b200_mesh(self.ctx, mesh_id, C.byref(light), _fp(_fa(pos, 3)), C.byref(t) if t else None))
+
+    # ---- sort-first bands (C ABI: partition, NCCL exchange, barrier) ---------------------------
+    def tile_height(self):
+        return int(self.lib.dtr_b200_tile_height())
+
+    def band_rows(self, nranks, rank):
+        y0, y1 = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.dtr_b200_band_rows(self.height, nranks, rank, C.byref(y0), C.byref(y1)))
+        return y0.value, y1.value
+
+    def band_comm_init(self, unique_id, nranks, rank):
+        """ncclCommInitRank inside the library (unique_id: the 128 bytes rank 0 got from band_comm_unique_id)."""
+        buf = (C.c_uint8 * 128)(*unique_id)
+        self._ck(self.lib.dtr_b200_band_comm_init(self.ctx, buf, nranks, rank))
+
+    def band_comm_unique_id(self):
+        buf = (C.c_uint8 * 128)()
+        self._ck(self.lib.dtr_b200_band_comm_unique_id(buf))
+        return bytes(buf)
+
+    def band_comm_init_torch(self, dist, group=None):
+        """Bootstrap the library's own NCCL communicator over an existing torch.distributed group:
+        rank 0's ncclUniqueId is broadcast, every rank calls dtr_b200_band_comm_init."""
+        import torch
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        buf = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            buf.copy_(torch.tensor(list(self.band_comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, src=0, group=group)
+        self.band_comm_init(bytes(buf.cpu().tolist()), world, rank)
+
+    def gather_bands(self, frame=0, dst=0):
+        """dtr_b200_gather_bands: grouped ncclSend/ncclRecv of every rank's band rows into rank dst's planes."""
+        self._ck(self.lib.dtr_b200_gather_bands(self.ctx, frame, dst))
+
+    def band_barrier(self):
+        self._ck(self.lib.dtr_b200_band_barrier(self.ctx))
 
     # ---- frame -------------------------------------------------------------------------------
     def set_target(self, frame):

@@ -20,6 +20,7 @@
 #include "../../include/dtr_b200.h"
 #include "dtr_host_math.h"
 #include "dtr_kernels.h"
+#include "dtr_nccl.h"
 #include "dtr_records.h"
 
 using namespace dtr;
@@ -96,6 +97,12 @@ struct dtr_b200_ctx
 	void        *ipcColor = nullptr, *ipcDepth = nullptr; // mappings opened from IPC handles
 	Geometry     geom{};
 	int          target = 0;
+	LaunchLimits limits{}; // this context's device: SM count and resident raster CTAs (queried at create)
+	// sort-first band exchange behind the C ABI (dtr_b200_band_comm_init / _attach)
+	NcclComm     comm = nullptr;
+	bool         ownComm = false;
+	int          commRanks = 0, commRank = -1;
+	float       *dToken = nullptr; // the barrier's 4-byte all-reduce buffer
 
 	std::vector<FrameHost> frames;
 	std::vector<RecItem>   rec;
@@ -422,7 +429,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 		B.listCapacity = (uint32_t)std::min({S.lists.cap / sizeof(uint32_t), S.listBounds.cap / (2 * sizeof(uint32_t)), S.listZ.cap / sizeof(int32_t)});
 		B.groupRows    = 0;
 		B.g            = g;
-		launch_bin(B, pre);
+		launch_bin(B, c->limits, pre);
 		c->launches++;
 	}
 	if ((rc = mark(c, pre))) return rc;
@@ -455,7 +462,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	R.smallTilesMin  = 0;
 	R.g          = g;
 	if ((rc = mark(c, c->stream))) return rc;
-	launch_raster(R, c->stream);
+	launch_raster(R, c->limits, c->stream);
 	c->launches++;
 	if ((rc = mark(c, c->stream))) return rc;
 	CU(cudaEventRecord(S.rasterDone, c->stream));
@@ -641,6 +648,8 @@ int dtr_b200_create(int device, int width, int height, int numFrames, dtr_b200_c
 			return DTR_B200_ERR_CUDA;
 		}
 	}
+	n->limits = query_launch_limits(device);
+	launch_init_tables(n->ownStream);
 	n->stream = n->ownStream;
 	n->outColor = n->dColor;
 	n->outDepth = n->dDepth;
@@ -675,6 +684,8 @@ void dtr_b200_destroy(dtr_b200_ctx *c)
 		if (ps.rasterDone) cudaEventDestroy(ps.rasterDone);
 	}
 	for (DevBuf *b : bufs) cudaFree(b->p);
+	if (c->comm && c->ownComm && nccl_api().ok) nccl_api().CommDestroy(c->comm);
+	cudaFree(c->dToken);
 	if (c->ipcColor) cudaIpcCloseMemHandle(c->ipcColor);
 	if (c->ipcDepth) cudaIpcCloseMemHandle(c->ipcDepth);
 	cudaFree(c->dColor);
@@ -716,7 +727,11 @@ int dtr_b200_set_band(dtr_b200_ctx *c, int y0, int y1)
 {
 	if (!c) return DTR_B200_ERR_ARG;
 	if (y0 < 0 || y1 > c->height || y0 >= y1 || (y0 % TILE_H) != 0 || ((y1 % TILE_H) != 0 && y1 != c->height))
-		return fail(c, DTR_B200_ERR_ARG, "band must be tile aligned (multiples of 32 rows, or end at height)");
+	{
+		char msg[128];
+		snprintf(msg, sizeof(msg), "band must be tile aligned (multiples of %d rows, or end at height)", TILE_H);
+		return fail(c, DTR_B200_ERR_ARG, msg);
+	}
 	CU(cudaSetDevice(c->device));
 	int rc = do_flush(c);
 	if (rc) return rc;
@@ -733,8 +748,14 @@ int dtr_b200_upload_texture(dtr_b200_ctx *c, const uint8_t *texels, int width, i
 	CU(cudaSetDevice(c->device));
 	uint32_t *d     = nullptr;
 	size_t    bytes = (size_t)width * height * 4;
-	CU(cudaMalloc((void **)&d, bytes));
+	// The nearest-texel fetch clamps u, v to [0, 1] and indexes (int)(v*h) * w + (int)(u*w) like the
+	// reference (DTRendererRender.cpp:1196-1203): v == 1 lands on row h, u == 1 one texel further.  The
+	// reference reads whatever follows its bitmap there; this allocation carries one spare row plus
+	// one texel of zeros so that the same read stays inside it (in-range results are unaffected).
+	const size_t padBytes = ((size_t)width + 1) * 4;
+	CU(cudaMalloc((void **)&d, bytes + padBytes));
 	CU(cudaMemcpy(d, texels, bytes, cudaMemcpyHostToDevice));
+	CU(cudaMemset((uint8_t *)d + bytes, 0, padBytes));
 	c->textures.push_back(TexDesc{d, width, height});
 	{
 		// 255 * (1/255.0f) == 1.0f and 1.0f^2 == 1.0f in fp32, so an all-white opaque texture leaves
@@ -760,6 +781,25 @@ int dtr_b200_upload_texture(dtr_b200_ctx *c, const uint8_t *texels, int width, i
 	return DTR_B200_OK;
 }
 
+int dtr_b200_update_texture(dtr_b200_ctx *c, int texId, const uint8_t *texels)
+{
+	if (!c || !texels) return DTR_B200_ERR_ARG;
+	if (texId < 0 || texId >= (int)c->textures.size()) return fail(c, DTR_B200_ERR_ARG, "texId out of range");
+	CU(cudaSetDevice(c->device));
+	int rc = do_flush(c); // draw calls recorded so far sample the old contents
+	if (rc) return rc;
+	CU(cudaStreamSynchronize(c->preStream));
+	CU(cudaStreamSynchronize(c->stream));
+	const TexDesc &td    = c->textures[texId];
+	const size_t   count = (size_t)td.w * td.h;
+	CU(cudaMemcpy(const_cast<uint32_t *>(td.texels), texels, count * 4, cudaMemcpyHostToDevice));
+	bool white = true;
+	for (size_t i = 0; i < count * 4 && white; i++) white = (texels[i] == 0xFF);
+	c->texIsWhite[texId] = white ? 1 : 0;
+	c->last.valid        = false; // a replay would keep the old "textured" decision
+	return DTR_B200_OK;
+}
+
 int dtr_b200_upload_bitmap_straight(dtr_b200_ctx *c, const uint8_t *rgba, int width, int height, int *texId)
 {
 	// upload the straight-alpha texels, then run DTRAsset_LoadBitmap's premultiply pass on the device
@@ -781,6 +821,30 @@ int dtr_b200_read_texture(dtr_b200_ctx *c, int texId, uint8_t *rgba)
 	return DTR_B200_OK;
 }
 
+namespace
+{
+// vertexes / texUV / normals of a DTRMesh, as they are (DTRendererAsset.h:27-41)
+int upload_mesh_arrays(dtr_b200_ctx *c, MeshAsset &a, const float *vertexes, uint32_t nV, const float *texUV, uint32_t nT,
+                       const float *normals, uint32_t nN)
+{
+	CU(cudaMalloc((void **)&a.vertexes, sizeof(float) * 4 * nV));
+	CU(cudaMalloc((void **)&a.texUV, sizeof(float) * 3 * nT));
+	CU(cudaMalloc((void **)&a.normals, sizeof(float) * 3 * nN));
+	CU(cudaMemcpy(a.vertexes, vertexes, sizeof(float) * 4 * nV, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(a.texUV, texUV, sizeof(float) * 3 * nT, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(a.normals, normals, sizeof(float) * 3 * nN, cudaMemcpyHostToDevice));
+	return 0;
+}
+void free_mesh(MeshAsset &a)
+{
+	cudaFree(a.vertexes);
+	cudaFree(a.texUV);
+	cudaFree(a.normals);
+	cudaFree(a.faces);
+	a = MeshAsset();
+}
+} // namespace
+
 int dtr_b200_upload_mesh(dtr_b200_ctx *c, const dtr_b200_mesh_desc *m, int texId, int *meshId)
 {
 	if (!c || !meshId) return DTR_B200_ERR_ARG;
@@ -798,14 +862,73 @@ int dtr_b200_upload_mesh(dtr_b200_ctx *c, const dtr_b200_mesh_desc *m, int texId
 	MeshAsset a;
 	a.numFaces = m->numFaces;
 	a.texId    = texId;
-	CU(cudaMalloc((void **)&a.vertexes, sizeof(float) * 4 * m->numVertexes));
-	CU(cudaMalloc((void **)&a.texUV, sizeof(float) * 3 * m->numTexUV));
-	CU(cudaMalloc((void **)&a.normals, sizeof(float) * 3 * m->numNormals));
+	int rc = upload_mesh_arrays(c, a, m->vertexes, m->numVertexes, m->texUV, m->numTexUV, m->normals, m->numNormals);
+	if (rc)
+	{
+		free_mesh(a);
+		return rc;
+	}
 	CU(cudaMalloc((void **)&a.faces, sizeof(int32_t) * 9 * m->numFaces));
-	CU(cudaMemcpy(a.vertexes, m->vertexes, sizeof(float) * 4 * m->numVertexes, cudaMemcpyHostToDevice));
-	CU(cudaMemcpy(a.texUV, m->texUV, sizeof(float) * 3 * m->numTexUV, cudaMemcpyHostToDevice));
-	CU(cudaMemcpy(a.normals, m->normals, sizeof(float) * 3 * m->numNormals, cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(a.faces, m->faces, sizeof(int32_t) * 9 * m->numFaces, cudaMemcpyHostToDevice));
+	c->meshes.push_back(a);
+	*meshId = (int)c->meshes.size() - 1;
+	return DTR_B200_OK;
+}
+
+int dtr_b200_upload_mesh_faces(dtr_b200_ctx *c, const dtr_b200_mesh_faces_desc *m, int texId, int *meshId)
+{
+	static_assert(sizeof(dtr_b200_mesh_face) == 48, "dtr_b200_mesh_face must mirror DTRMeshFace");
+	if (!c || !meshId) return DTR_B200_ERR_ARG;
+	if (!m || !m->vertexes || !m->texUV || !m->normals || !m->faces || !m->numFaces || !m->arena || !m->arenaBytes)
+		return fail(c, DTR_B200_ERR_ARG, "mesh needs vertexes, texUV, normals, faces and the arena block of the index arrays");
+	if (texId >= (int)c->textures.size()) return fail(c, DTR_B200_ERR_ARG, "texId out of range");
+	CU(cudaSetDevice(c->device));
+	MeshAsset a;
+	a.numFaces = m->numFaces;
+	a.texId    = texId;
+	int rc = upload_mesh_arrays(c, a, m->vertexes, m->numVertexes, m->texUV, m->numTexUV, m->normals, m->numNormals);
+	uint8_t  *dFaces = nullptr, *dArena = nullptr;
+	uint32_t *dErr = nullptr, err = 0;
+	cudaError_t e = cudaSuccess;
+	if (!rc && ((e = cudaMalloc((void **)&a.faces, sizeof(int32_t) * 9 * m->numFaces)) != cudaSuccess ||
+	            (e = cudaMalloc((void **)&dFaces, sizeof(dtr_b200_mesh_face) * (size_t)m->numFaces)) != cudaSuccess ||
+	            (e = cudaMalloc((void **)&dArena, m->arenaBytes)) != cudaSuccess ||
+	            (e = cudaMalloc((void **)&dErr, sizeof(uint32_t))) != cudaSuccess ||
+	            (e = cudaMemsetAsync(dErr, 0, sizeof(uint32_t), c->stream)) != cudaSuccess ||
+	            // one copy each: the DTRMeshFace array and the block its pointers lead into
+	            (e = cudaMemcpyAsync(dFaces, m->faces, sizeof(dtr_b200_mesh_face) * (size_t)m->numFaces, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
+	            (e = cudaMemcpyAsync(dArena, m->arena, m->arenaBytes, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess))
+		rc = fail(c, DTR_B200_ERR_CUDA, "uploading the mesh's face arrays", e);
+	if (!rc)
+	{
+		FlattenParams F;
+		F.faces       = dFaces;
+		F.arena       = dArena;
+		F.hostArena   = (uint64_t)(uintptr_t)m->arena;
+		F.arenaBytes  = (uint64_t)m->arenaBytes;
+		F.numFaces    = m->numFaces;
+		F.numVertexes = m->numVertexes;
+		F.numTexUV    = m->numTexUV;
+		F.numNormals  = m->numNormals;
+		F.out         = a.faces;
+		F.error       = dErr;
+		launch_flatten_faces(F, c->stream);
+		c->launches++;
+		if ((e = cudaGetLastError()) != cudaSuccess ||
+		    (e = cudaMemcpyAsync(&err, dErr, sizeof(err), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+		    (e = cudaStreamSynchronize(c->stream)) != cudaSuccess)
+			rc = fail(c, DTR_B200_ERR_CUDA, "flattening the mesh's face arrays", e);
+		else if (err)
+			rc = fail(c, DTR_B200_ERR_ARG, "malformed face: index arrays outside the arena, counts not 3 / >=3 / 3, or an index out of range");
+	}
+	cudaFree(dFaces);
+	cudaFree(dArena);
+	cudaFree(dErr);
+	if (rc)
+	{
+		free_mesh(a);
+		return rc;
+	}
 	c->meshes.push_back(a);
 	*meshId = (int)c->meshes.size() - 1;
 	return DTR_B200_OK;
@@ -831,11 +954,18 @@ int dtr_b200_begin_frame(dtr_b200_ctx *c, int frame, const uint32_t *hostColor, 
 	}
 	size_t     plane = (size_t)c->width * c->height;
 	FrameHost &fh    = c->frames[frame];
-	fh.pendingInit   = 0;
+	// a dtr_b200_clear recorded as the frame's on-chip colour init stays pending (the reference's
+	// Clear writes the colour buffer, the frame start only resets depth) unless colour is uploaded now
+	fh.pendingInit &= FI_COLOR_CLEAR;
+	// an asynchronous readback of this frame may still be in flight on the copy stream
+	if ((hostZ || hostColor) && frame >= c->readLo && frame < c->readHi) CU(cudaStreamWaitEvent(c->stream, c->copyDone, 0));
 	if (hostZ) CU(cudaMemcpyAsync(c->outDepth + plane * frame, hostZ, plane * sizeof(float), cudaMemcpyHostToDevice, c->stream));
 	else fh.pendingInit |= FI_Z_RESET;
 	if (hostColor)
+	{
+		fh.pendingInit &= ~(uint32_t)FI_COLOR_CLEAR;
 		CU(cudaMemcpyAsync(c->outColor + plane * frame, hostColor, plane * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+	}
 	c->target = frame;
 	return DTR_B200_OK;
 }
@@ -1030,6 +1160,138 @@ int dtr_b200_enable_peer_access(dtr_b200_ctx *c, int peerDevice)
 	CU(e);
 	return DTR_B200_OK;
 }
+
+// ---- sort-first bands behind the C ABI: partition, exchange (NCCL) and barrier -------------------
+int dtr_b200_tile_height(void) { return TILE_H; }
+
+int dtr_b200_band_rows(int height, int nranks, int rank, int *y0, int *y1)
+{
+	if (height <= 0 || nranks <= 0 || rank < 0 || rank >= nranks || !y0 || !y1) return DTR_B200_ERR_ARG;
+	const int tiles = (height + TILE_H - 1) / TILE_H, base = tiles / nranks, rem = tiles % nranks;
+	const int t0 = rank * base + std::min(rank, rem), t1 = t0 + base + (rank < rem ? 1 : 0);
+	*y0 = std::min(t0 * TILE_H, height);
+	*y1 = std::min(t1 * TILE_H, height);
+	return DTR_B200_OK;
+}
+
+#define NC(call)                                                                                          \
+	do                                                                                                    \
+	{                                                                                                     \
+		int r_ = (call);                                                                                  \
+		if (r_ != 0)                                                                                      \
+		{                                                                                                 \
+			std::string m_ = std::string(#call ": ") + (N.GetErrorString ? N.GetErrorString(r_) : "NCCL error"); \
+			return fail(c, DTR_B200_ERR_CUDA, m_.c_str());                                                \
+		}                                                                                                 \
+	} while (0)
+
+int dtr_b200_band_comm_unique_id(uint8_t id[DTR_B200_NCCL_ID_BYTES])
+{
+	static_assert(sizeof(NcclUniqueId) == DTR_B200_NCCL_ID_BYTES, "ncclUniqueId size");
+	dtr_b200_ctx  *c = nullptr;
+	const NcclApi &N = nccl_api();
+	if (!id) return DTR_B200_ERR_ARG;
+	if (!N.ok) return fail(c, DTR_B200_ERR_CUDA, N.err.c_str());
+	NcclUniqueId u;
+	NC(N.GetUniqueId(&u));
+	memcpy(id, &u, sizeof(u));
+	return DTR_B200_OK;
+}
+
+namespace
+{
+int adopt_comm(dtr_b200_ctx *c, NcclComm comm, bool own, int nranks, int rank)
+{
+	if (c->comm && c->ownComm) nccl_api().CommDestroy(c->comm);
+	c->comm      = comm;
+	c->ownComm   = own;
+	c->commRanks = nranks;
+	c->commRank  = rank;
+	if (!c->dToken)
+	{
+		CU(cudaMalloc((void **)&c->dToken, sizeof(float)));
+		CU(cudaMemset(c->dToken, 0, sizeof(float)));
+	}
+	return DTR_B200_OK;
+}
+} // namespace
+
+int dtr_b200_band_comm_init(dtr_b200_ctx *c, const uint8_t id[DTR_B200_NCCL_ID_BYTES], int nranks, int rank)
+{
+	if (!c || !id || nranks <= 0 || rank < 0 || rank >= nranks) return DTR_B200_ERR_ARG;
+	const NcclApi &N = nccl_api();
+	if (!N.ok) return fail(c, DTR_B200_ERR_CUDA, N.err.c_str());
+	CU(cudaSetDevice(c->device));
+	NcclUniqueId u;
+	memcpy(&u, id, sizeof(u));
+	NcclComm comm = nullptr;
+	NC(N.CommInitRank(&comm, nranks, u, rank));
+	return adopt_comm(c, comm, true, nranks, rank);
+}
+
+int dtr_b200_band_comm_attach(dtr_b200_ctx *c, void *ncclComm, int nranks, int rank)
+{
+	if (!c || !ncclComm || nranks <= 0 || rank < 0 || rank >= nranks) return DTR_B200_ERR_ARG;
+	const NcclApi &N = nccl_api();
+	if (!N.ok) return fail(c, DTR_B200_ERR_CUDA, N.err.c_str());
+	CU(cudaSetDevice(c->device));
+	return adopt_comm(c, (NcclComm)ncclComm, false, nranks, rank);
+}
+
+int dtr_b200_gather_bands(dtr_b200_ctx *c, int frame, int dstRank)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (!c->comm) return fail(c, DTR_B200_ERR_ARG, "no band communicator (dtr_b200_band_comm_init / _attach)");
+	if (!valid_frame(c, frame) || dstRank < 0 || dstRank >= c->commRanks) return fail(c, DTR_B200_ERR_ARG, "frame or dstRank out of range");
+	const NcclApi &N = nccl_api();
+	CU(cudaSetDevice(c->device));
+	int rc = do_flush(c);
+	if (rc) return rc;
+	const size_t plane = (size_t)c->width * c->height;
+	uint32_t    *col   = c->outColor + plane * frame;
+	float       *dep   = c->outDepth + plane * frame;
+	if (c->commRank != dstRank)
+	{
+		// the rows this context rasterises must be its rank's band of THE partition
+		int y0 = 0, y1 = 0;
+		dtr_b200_band_rows(c->height, c->commRanks, c->commRank, &y0, &y1);
+		if (y1 > y0 && (c->geom.bandTileY0 * TILE_H != y0 || std::min(c->geom.bandTileY1 * TILE_H, c->height) != y1))
+			return fail(c, DTR_B200_ERR_ARG, "this context's band is not dtr_b200_band_rows(height, nranks, rank)");
+	}
+	NC(N.GroupStart());
+	for (int r = 0; r < c->commRanks; r++)
+	{
+		int y0 = 0, y1 = 0;
+		dtr_b200_band_rows(c->height, c->commRanks, r, &y0, &y1);
+		if (r == dstRank || y1 <= y0) continue;
+		const size_t off = (size_t)y0 * c->width, n = (size_t)(y1 - y0) * c->width; // rows are contiguous: one message per plane
+		if (c->commRank == dstRank)
+		{
+			NC(N.Recv(col + off, n, NCCL_UINT32, r, c->comm, c->stream));
+			NC(N.Recv(dep + off, n, NCCL_FLOAT32, r, c->comm, c->stream));
+		}
+		else if (c->commRank == r)
+		{
+			NC(N.Send(col + off, n, NCCL_UINT32, dstRank, c->comm, c->stream));
+			NC(N.Send(dep + off, n, NCCL_FLOAT32, dstRank, c->comm, c->stream));
+		}
+	}
+	NC(N.GroupEnd());
+	return DTR_B200_OK;
+}
+
+int dtr_b200_band_barrier(dtr_b200_ctx *c)
+{
+	if (!c) return DTR_B200_ERR_ARG;
+	if (!c->comm) return fail(c, DTR_B200_ERR_ARG, "no band communicator (dtr_b200_band_comm_init / _attach)");
+	const NcclApi &N = nccl_api();
+	CU(cudaSetDevice(c->device));
+	int rc = do_flush(c);
+	if (rc) return rc;
+	NC(N.AllReduce(c->dToken, c->dToken, 1, NCCL_FLOAT32, NCCL_SUM, c->comm, c->stream));
+	return DTR_B200_OK;
+}
+#undef NC
 
 int dtr_b200_frame_device_ptrs(dtr_b200_ctx *c, int frame, void **color, void **z)
 {

@@ -42,6 +42,7 @@ struct ScanParams
 	uint32_t           *numBusy;  // number of tiles with primitives
 };
 
+// one look-back word per chunk plus one more: the ticket counter that hands out chunk ids
 inline uint32_t scan_status_words(uint32_t n) { return (n + SCAN_CHUNK - 1) / SCAN_CHUNK + 1; }
 
 // segs > 1 only: per tile, the exclusive prefix of its segment counts and their sum
@@ -94,14 +95,38 @@ struct RasterParams
 	Geometry            g;
 };
 
+// Per-device launch limits, queried once per context (dtr_b200_create) on ITS device: a process may
+// hold contexts on several GPUs.
+struct LaunchLimits
+{
+	int sms          = 148;
+	int residentCtas = 148; // raster CTAs resident on the whole device (sms x CTAs per SM)
+};
+LaunchLimits query_launch_limits(int device);
+void         launch_init_tables(cudaStream_t s); // per-device lookup tables of the raster kernel (once per context)
+
+// DTRMesh's per-face index arrays (DTRendererAsset.h:16-26) flattened on the device: faces[] holds
+// HOST pointers into the arena block, which was uploaded as one copy (see dtr_b200_upload_mesh_faces).
+struct FlattenParams
+{
+	const uint8_t *faces;      // device copy of DTRMeshFace[numFaces] (48 bytes each)
+	const uint8_t *arena;      // device copy of the host arena block
+	uint64_t       hostArena;  // host address of the block
+	uint64_t       arenaBytes;
+	uint32_t       numFaces, numVertexes, numTexUV, numNormals;
+	int32_t       *out;        // i32[numFaces][9]
+	uint32_t      *error;      // != 0: some face was malformed
+};
+void launch_flatten_faces(const FlattenParams &P, cudaStream_t s);
+
 void launch_setup(const SetupParams &P, cudaStream_t s);
 // Scans the tile counts (-> totals[0]); the offsets array gets one extra trailing entry holding the
 // total.  Also zeroes the raster work counter and writes the work order.
 void launch_scan(const ScanParams &P, cudaStream_t s);
 void launch_tile_sum(const TileSumParams &P, cudaStream_t s);
 void launch_selftest_sqrt(unsigned long long *mismatches, cudaStream_t s);
-void launch_bin(const BinParams &P, cudaStream_t s);
-void launch_raster(const RasterParams &P, cudaStream_t s);
+void launch_bin(const BinParams &P, const LaunchLimits &L, cudaStream_t s);
+void launch_raster(const RasterParams &P, const LaunchLimits &L, cudaStream_t s);
 void launch_premultiply(uint32_t *pixels, size_t count, cudaStream_t s);
 void launch_pack_bgr24(const uint32_t *color, uint32_t *out, int width, size_t rows, int pitchWords, cudaStream_t s);
 

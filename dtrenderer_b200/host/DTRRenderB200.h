@@ -18,9 +18,12 @@
 //     DTRRenderB200_BeginFrame(renderBuffer)  after the per-frame z-buffer reset
 //     DTRRenderB200_EndFrame(renderBuffer)    before the platform presents renderBuffer->memory
 //
-// The binding owns one dtr_b200_ctx per DTRRenderBuffer (created on first use) and caches the
-// uploads of DTRMesh / DTRBitmap by address.  No reference source is modified or copied; see
-// INTEGRATION.md for the three-line patch that switches the renderer over.
+// The binding owns one dtr_b200_ctx per DTRRenderBuffer (created on first use, on the device chosen
+// with DTRB200_SetDevice, default 0) and caches the uploads of DTRMesh / DTRBitmap / DTRFont by
+// address AND a cheap content fingerprint (dimensions / counts plus a strided sample of the bytes): an
+// asset whose memory is reused for something else is uploaded again.  An asset edited in place in a
+// way the sample misses is refreshed with DTRRenderB200_Invalidate(ptr).  No reference source is
+// modified or copied; see INTEGRATION.md for the three-line patch that switches the renderer over.
 #ifndef DTR_RENDER_B200_H
 #define DTR_RENDER_B200_H
 
@@ -33,13 +36,37 @@
 #define DTR_B200_DEBUG_MARKERS 0
 #endif
 
+struct DTRB200Cached
+{
+	int      id   = -1;
+	uint64_t mark = 0; // content fingerprint at upload time
+};
+
 struct DTRB200Binding
 {
-	dtr_b200_ctx                  *ctx = nullptr;
-	std::map<const void *, int>    textures; // DTRBitmap::memory -> texId
-	std::map<const DTRMesh *, int> meshes;
-	std::map<const void *, int>    fonts; // DTRFont::bitmap -> fontId
+	dtr_b200_ctx                         *ctx = nullptr;
+	std::map<const void *, DTRB200Cached> textures; // DTRBitmap::memory -> texId
+	std::map<const void *, DTRB200Cached> meshes;   // DTRMesh * -> meshId
+	std::map<const void *, DTRB200Cached> fonts;    // DTRFont::bitmap -> fontId
 };
+
+inline int &DTRB200_Device()
+{
+	static int device = 0;
+	return device;
+}
+// Which CUDA device new bindings are created on (one host thread per device).
+inline void DTRB200_SetDevice(int device) { DTRB200_Device() = device; }
+
+// FNV-1a over the sizes and at most 4096 bytes sampled evenly from the asset: cheap per draw call.
+inline uint64_t DTRB200_Fingerprint(const void *data, size_t bytes, uint64_t seed)
+{
+	uint64_t       h = 1469598103934665603ull ^ seed;
+	const uint8_t *p = (const uint8_t *)data;
+	const size_t   step = bytes > 4096 ? bytes / 4096 : 1;
+	for (size_t i = 0; i < bytes; i += step) h = (h ^ p[i]) * 1099511628211ull;
+	return (h ^ bytes) * 1099511628211ull;
+}
 
 inline std::map<const DTRRenderBuffer *, DTRB200Binding> &DTRB200_Bindings()
 {
@@ -53,7 +80,7 @@ inline DTRB200Binding *DTRB200_Bind(const DTRRenderBuffer *rb)
 	DTRB200Binding &b = DTRB200_Bindings()[rb];
 	if (!b.ctx)
 	{
-		if (dtr_b200_create(0, rb->width, rb->height, 1, &b.ctx) != DTR_B200_OK) return nullptr;
+		if (dtr_b200_create(DTRB200_Device(), rb->width, rb->height, 1, &b.ctx) != DTR_B200_OK) return nullptr;
 		// DTR_B200_DEBUG_MARKERS 1 reproduces the overlay of the reference's default
 		// (DTR_DEBUG_RENDER 1) build: bounding boxes, rotated outlines, bitmap corner markers
 		dtr_b200_set_debug_markers(b.ctx, DTR_B200_DEBUG_MARKERS);
@@ -70,12 +97,26 @@ inline dtr_b200_transform DTRB200_Transform(const DTRRenderTransform &t)
 inline int DTRB200_Texture(DTRB200Binding *b, const DTRBitmap *bmp)
 {
 	if (!bmp || !bmp->memory) return -1;
-	auto it = b->textures.find(bmp->memory);
-	if (it != b->textures.end()) return it->second;
+	const size_t   bytes = (size_t)bmp->dim.w * bmp->dim.h * bmp->bytesPerPixel;
+	const uint64_t mark  = DTRB200_Fingerprint(bmp->memory, bytes, ((uint64_t)bmp->dim.w << 32) | (uint32_t)bmp->dim.h);
+	auto           it    = b->textures.find(bmp->memory);
+	if (it != b->textures.end() && it->second.mark == mark) return it->second.id;
 	int id = -1;
 	if (dtr_b200_upload_texture(b->ctx, bmp->memory, bmp->dim.w, bmp->dim.h, bmp->bytesPerPixel, &id) != DTR_B200_OK) return -1;
-	b->textures[bmp->memory] = id;
+	b->textures[bmp->memory] = DTRB200Cached{id, mark};
 	return id;
+}
+
+// Forget what was uploaded from this address (DTRBitmap::memory, a DTRMesh *, DTRFont::bitmap) in every
+// binding: the next draw call that uses it uploads it again.
+inline void DTRRenderB200_Invalidate(const void *asset)
+{
+	for (auto &kv : DTRB200_Bindings())
+	{
+		kv.second.textures.erase(asset);
+		kv.second.meshes.erase(asset);
+		kv.second.fonts.erase(asset);
+	}
 }
 
 // Frame hooks ------------------------------------------------------------------------------------
@@ -126,28 +167,54 @@ inline void DTRRenderB200_Mesh(DTRRenderContext context, PlatformJobQueue *const
 	if (!mesh || !context.renderBuffer || !context.tempStack || !context.api || !jobQueue) return;
 	DTRB200Binding *b = DTRB200_Bind(context.renderBuffer);
 	if (!b) return;
-	int  meshId = -1;
-	auto it     = b->meshes.find(mesh);
-	if (it != b->meshes.end()) meshId = it->second;
+	int            meshId = -1;
+	const uint64_t mark   = DTRB200_Fingerprint(mesh->vertexes, sizeof(DqnV4) * (size_t)mesh->numVertexes,
+	                                            ((uint64_t)mesh->numFaces << 32) | mesh->numVertexes) ^
+	                      DTRB200_Fingerprint(mesh->faces, sizeof(DTRMeshFace) * (size_t)mesh->numFaces, mesh->numNormals);
+	auto it = b->meshes.find(mesh);
+	if (it != b->meshes.end() && it->second.mark == mark) meshId = it->second.id;
 	else
 	{
-		// flatten the per-face index arrays (DTRendererAsset.h:16-26) once
-		std::vector<int32_t> faces((size_t)mesh->numFaces * 9);
-		for (u32 i = 0; i < mesh->numFaces; i++)
+		const int texId = DTRB200_Texture(b, &mesh->tex);
+		// DTRAsset_LoadWavefrontObj leaves the whole mesh in ONE memory block -- vertexes, texUV, normals,
+		// faces, then every face's three index arrays in order (DTRendererAsset.cpp:509-578).  If this mesh
+		// looks like that, the block is uploaded as it is and the index table is flattened on the device
+		// (which also verifies that every pointer stays inside the block); otherwise, or if that check
+		// fails, the per-face arrays are gathered here.
+		static_assert(sizeof(dtr_b200_mesh_face) == sizeof(DTRMeshFace), "dtr_b200_mesh_face mirrors DTRMeshFace");
+		bool uploaded = false;
+		if (mesh->numFaces)
 		{
-			const DTRMeshFace &f = mesh->faces[i];
-			if (f.numVertexIndex != 3 || f.numNormalIndex != 3 || f.numTexIndex < 3) return; // reference asserts
-			for (int k = 0; k < 3; k++)
+			const DTRMeshFace &last  = mesh->faces[mesh->numFaces - 1];
+			const uint8_t     *begin = (const uint8_t *)mesh->vertexes;
+			const uint8_t     *end   = (const uint8_t *)(last.normalIndex + last.numNormalIndex);
+			if (last.normalIndex && end > begin && (const uint8_t *)mesh->faces > begin && (const uint8_t *)mesh->faces < end)
 			{
-				faces[9 * i + k]     = f.vertexIndex[k];
-				faces[9 * i + 3 + k] = f.texIndex[k];
-				faces[9 * i + 6 + k] = f.normalIndex[k];
+				dtr_b200_mesh_faces_desc d = {(const float *)mesh->vertexes, mesh->numVertexes, (const float *)mesh->texUV,
+				                              mesh->numTexUV,                (const float *)mesh->normals, mesh->numNormals,
+				                              (const dtr_b200_mesh_face *)mesh->faces, mesh->numFaces, begin, (size_t)(end - begin)};
+				uploaded = dtr_b200_upload_mesh_faces(b->ctx, &d, texId, &meshId) == DTR_B200_OK;
 			}
 		}
-		dtr_b200_mesh_desc d = {(const float *)mesh->vertexes, mesh->numVertexes, (const float *)mesh->texUV, mesh->numTexUV,
-		                        (const float *)mesh->normals,  mesh->numNormals,  faces.data(),               mesh->numFaces};
-		if (dtr_b200_upload_mesh(b->ctx, &d, DTRB200_Texture(b, &mesh->tex), &meshId) != DTR_B200_OK) return;
-		b->meshes[mesh] = meshId;
+		if (!uploaded)
+		{
+			std::vector<int32_t> faces((size_t)mesh->numFaces * 9);
+			for (u32 i = 0; i < mesh->numFaces; i++)
+			{
+				const DTRMeshFace &f = mesh->faces[i];
+				if (f.numVertexIndex != 3 || f.numNormalIndex != 3 || f.numTexIndex < 3) return; // reference asserts
+				for (int k = 0; k < 3; k++)
+				{
+					faces[9 * i + k]     = f.vertexIndex[k];
+					faces[9 * i + 3 + k] = f.texIndex[k];
+					faces[9 * i + 6 + k] = f.normalIndex[k];
+				}
+			}
+			dtr_b200_mesh_desc d = {(const float *)mesh->vertexes, mesh->numVertexes, (const float *)mesh->texUV, mesh->numTexUV,
+			                        (const float *)mesh->normals,  mesh->numNormals,  faces.data(),               mesh->numFaces};
+			if (dtr_b200_upload_mesh(b->ctx, &d, texId, &meshId) != DTR_B200_OK) return;
+		}
+		b->meshes[mesh] = DTRB200Cached{meshId, mark};
 	}
 	dtr_b200_light     l = {(int32_t)lighting.mode, {lighting.vector.x, lighting.vector.y, lighting.vector.z},
 	                        {lighting.color.r, lighting.color.g, lighting.color.b, lighting.color.a}};
@@ -183,15 +250,17 @@ inline void DTRRenderB200_Text(DTRRenderContext context, const DTRFont font, Dqn
 	static_assert(sizeof(dtr_b200_packedchar) == sizeof(stbtt_packedchar), "packed char layout");
 	DTRB200Binding *b = DTRB200_Bind(context.renderBuffer);
 	if (!b) return;
-	int  id = -1;
-	auto it = b->fonts.find(font.bitmap);
-	if (it != b->fonts.end()) id = it->second;
+	int            id   = -1;
+	const uint64_t mark = DTRB200_Fingerprint(font.bitmap, (size_t)font.bitmapDim.w * font.bitmapDim.h,
+	                                          ((uint64_t)font.bitmapDim.w << 32) | (uint32_t)font.bitmapDim.h);
+	auto           it   = b->fonts.find(font.bitmap);
+	if (it != b->fonts.end() && it->second.mark == mark) id = it->second.id;
 	else
 	{
 		if (dtr_b200_upload_font(b->ctx, font.bitmap, font.bitmapDim.w, font.bitmapDim.h, (const dtr_b200_packedchar *)font.atlas,
 		                         font.codepointRange.min, font.codepointRange.max, &id) != DTR_B200_OK)
 			return;
-		b->fonts[font.bitmap] = id;
+		b->fonts[font.bitmap] = DTRB200Cached{id, mark};
 	}
 	dtr_b200_text(b->ctx, id, pos.e, text, color.e, len);
 }

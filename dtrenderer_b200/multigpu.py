@@ -14,7 +14,7 @@ GPU; torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests) carries
 """
 import numpy as np
 
-TILE_H = 32  # dtr::TILE_H -- bands must start on a tile row
+TILE_H = 32  # default of dtr::TILE_H; callers with a loaded library pass dtr_b200_tile_height() instead
 
 
 def split_views(n_views, world, rank):
@@ -24,14 +24,16 @@ def split_views(n_views, world, rank):
     return list(range(start, start + base + (1 if rank < rem else 0)))
 
 
-def band_rows(height, world, rank):
+def band_rows(height, world, rank, tile_h=None):
     """Tile-aligned row band [y0, y1) of rank `rank`; bands tile [0, height) exactly, and trailing
-    ranks may get an empty band when there are fewer tile rows than ranks."""
-    tiles = (height + TILE_H - 1) // TILE_H
+    ranks may get an empty band when there are fewer tile rows than ranks.  The same partition as
+    dtr_b200_band_rows (tests/test_capi_boundary.py compares them); tile_h = dtr_b200_tile_height()."""
+    tile_h = tile_h or TILE_H
+    tiles = (height + tile_h - 1) // tile_h
     base, rem = divmod(tiles, world)
     t0 = rank * base + min(rank, rem)
     t1 = t0 + base + (1 if rank < rem else 0)
-    return min(t0 * TILE_H, height), min(t1 * TILE_H, height)
+    return min(t0 * tile_h, height), min(t1 * tile_h, height)
 
 
 class _DevicePtr:

@@ -15,6 +15,11 @@
  *   dtr_b200_end_frame          <- hand-back of the DTRRenderBuffer (DTRendererRender.h:14-25)
  *   dtr_b200_upload_mesh/_texture <- DTRMesh / DTRBitmap as produced by DTRendererAsset
  *                                    (DTRendererAsset.h:9-42); the loaders stay on the host.
+ *   dtr_b200_upload_mesh_faces  <- DTRMesh with its per-face index arrays as they lie in the asset
+ *                                    arena (DTRendererAsset.h:16-26, .cpp:509-578): flattened on the device
+ *   dtr_b200_gather_bands / dtr_b200_band_barrier <- replace the reference's only parallel mode, the
+ *                                    per-triangle job fan-out with its per-pixel lock
+ *                                    (DTRendererRender.cpp:1367-1393, 1162-1171), for sort-first bands
  *
  * Semantics.  Draw calls are RECORDED and executed in submission order per frame: the result of
  * a flush is the reference's single-threaded (`multithread=false`) in-order result -- coverage,
@@ -112,8 +117,13 @@ const char *dtr_b200_version(void);
 /* Use an existing cudaStream_t (e.g. the caller's current stream) instead of the context's own. */
 int         dtr_b200_set_stream(dtr_b200_ctx *ctx, void *cudaStream);
 /* Sort-first band split: only rows [y0,y1) are rasterised by this context (tile aligned: both
- * multiples of 32 or y1 == height).  Default is the whole frame. */
+ * multiples of dtr_b200_tile_height() or y1 == height).  Default is the whole frame. */
 int         dtr_b200_set_band(dtr_b200_ctx *ctx, int y0, int y1);
+/* Height in pixels of a screen tile of this build (32): the granularity of bands. */
+int         dtr_b200_tile_height(void);
+/* THE band partition: tile-aligned rows [*y0, *y1) of rank `rank` out of `nranks`; the bands tile
+ * [0, height) exactly, trailing ranks get an empty band when there are fewer tile rows than ranks. */
+int         dtr_b200_band_rows(int height, int nranks, int rank, int *y0, int *y1);
 
 /* ---- assets (device resident until destroy) ----------------------------------------------- */
 int dtr_b200_upload_texture(dtr_b200_ctx *ctx, const uint8_t *texels, int width, int height,
@@ -126,6 +136,42 @@ int dtr_b200_upload_texture(dtr_b200_ctx *ctx, const uint8_t *texels, int width,
 int dtr_b200_upload_bitmap_straight(dtr_b200_ctx *ctx, const uint8_t *rgba, int width, int height, int *texId);
 int dtr_b200_read_texture(dtr_b200_ctx *ctx, int texId, uint8_t *rgba);
 int dtr_b200_upload_mesh(dtr_b200_ctx *ctx, const dtr_b200_mesh_desc *mesh, int texId, int *meshId);
+/* The other half of SURVEY.md §8f rank 3: DTRMesh as DTRAsset_LoadWavefrontObj leaves it
+ * (DTRendererAsset.cpp:509-578) -- an array of DTRMeshFace, each pointing at three separately
+ * allocated i32 index arrays inside the asset arena -- flattened ON THE DEVICE.  `faces` is the
+ * DTRMeshFace array itself (dtr_b200_mesh_face is layout compatible with DTRMeshFace,
+ * DTRendererAsset.h:16-26); [arena, arena + arenaBytes) is the host memory block that contains every
+ * index array the faces point to (the reference's assetStack block).  The block and the face array are
+ * uploaded with one copy each and a gather kernel chases the (rebased) pointers into i32[numFaces][9];
+ * no per-face host loop.  Faces whose pointers leave the arena, whose counts are not 3/>=3/3 (the
+ * reference asserts, DTRendererRender.cpp:1440-1441) or whose indices are out of range make the call
+ * fail with DTR_B200_ERR_ARG. */
+typedef struct dtr_b200_mesh_face
+{
+	const int32_t *vertexIndex;
+	uint32_t       numVertexIndex;
+	const int32_t *texIndex;
+	uint32_t       numTexIndex;
+	const int32_t *normalIndex;
+	uint32_t       numNormalIndex;
+} dtr_b200_mesh_face;
+typedef struct dtr_b200_mesh_faces_desc
+{
+	const float              *vertexes; /* f32[numVertexes*4], w must be 1 */
+	uint32_t                  numVertexes;
+	const float              *texUV;    /* f32[numTexUV*3] */
+	uint32_t                  numTexUV;
+	const float              *normals;  /* f32[numNormals*3] */
+	uint32_t                  numNormals;
+	const dtr_b200_mesh_face *faces;    /* DTRMeshFace[numFaces] */
+	uint32_t                  numFaces;
+	const void               *arena;    /* host block containing every index array */
+	size_t                    arenaBytes;
+} dtr_b200_mesh_faces_desc;
+int dtr_b200_upload_mesh_faces(dtr_b200_ctx *ctx, const dtr_b200_mesh_faces_desc *mesh, int texId, int *meshId);
+/* Forget cached device copies after the host changed an asset in place: the texture / mesh keeps its
+ * id, its contents are uploaded again (same dimensions / counts required). */
+int dtr_b200_update_texture(dtr_b200_ctx *ctx, int texId, const uint8_t *texels);
 
 /* ---- frame -------------------------------------------------------------------------------- */
 int dtr_b200_set_target(dtr_b200_ctx *ctx, int frame);
@@ -181,6 +227,27 @@ int dtr_b200_export_frames(dtr_b200_ctx *ctx, uint8_t *colorHandle, uint8_t *dep
 int dtr_b200_open_peer_frames(dtr_b200_ctx *ctx, const uint8_t *colorHandle, const uint8_t *depthHandle);
 int dtr_b200_set_output_planes(dtr_b200_ctx *ctx, void *color, void *depth);
 int dtr_b200_enable_peer_access(dtr_b200_ctx *ctx, int peerDevice);
+/* Sort-first bands from a C/C++ host, no Python: the exchange step and its barrier behind the C ABI
+ * (SURVEY.md §8b/§8e).  NCCL is bound at run time (dlopen of libnccl.so.2 -- the copy already loaded
+ * into the process if there is one -- so the library has no link-time NCCL dependency).
+ *   dtr_b200_band_comm_unique_id  rank 0: a fresh ncclUniqueId (128 bytes) to hand to the other ranks
+ *   dtr_b200_band_comm_init       every rank: ncclCommInitRank on this context's device
+ *   dtr_b200_band_comm_attach     alternative: use a communicator the host already owns (an
+ *                                 ncclComm_t passed as void *; not destroyed with the context)
+ *   dtr_b200_gather_bands         flush, then one grouped ncclSend/ncclRecv on the context's stream:
+ *                                 every rank's band rows (dtr_b200_band_rows of its rank) of colour and
+ *                                 depth of `frame` land in the same rows of rank dstRank's planes.
+ *                                 The baseline exchange; the fused peer-memory write-back above is faster.
+ *   dtr_b200_band_barrier         stream-ordered barrier (a 4-byte ncclAllReduce on the context's
+ *                                 stream): after it completes on rank r, every rank's work enqueued
+ *                                 before its own barrier call -- e.g. the raster kernel that writes its
+ *                                 band into r's planes -- has finished. */
+#define DTR_B200_NCCL_ID_BYTES 128
+int dtr_b200_band_comm_unique_id(uint8_t id[DTR_B200_NCCL_ID_BYTES]);
+int dtr_b200_band_comm_init(dtr_b200_ctx *ctx, const uint8_t id[DTR_B200_NCCL_ID_BYTES], int nranks, int rank);
+int dtr_b200_band_comm_attach(dtr_b200_ctx *ctx, void *ncclComm, int nranks, int rank);
+int dtr_b200_gather_bands(dtr_b200_ctx *ctx, int frame, int dstRank);
+int dtr_b200_band_barrier(dtr_b200_ctx *ctx);
 /* Device pointers of a frame's planes (u32[W*H], f32[W*H]) for zero-copy consumers
  * (NCCL / peer access / torch views). */
 int dtr_b200_frame_device_ptrs(dtr_b200_ctx *ctx, int frame, void **color, void **z);

@@ -173,18 +173,34 @@ void dtro_mesh(dtro_ctx *c, const float *vertexes, int numVertexes, const float 
                const float lightVector[3], const float lightColor[4], const float pos[3], const float transform[7])
 {
 	Begin(c);
+	// the mesh in ONE block, laid out like DTRAsset_LoadWavefrontObj's model block
+	// (DTRendererAsset.cpp:509-578): vertexes | texUV | normals | faces | every face's three index arrays --
+	// the mirror then uploads the block as it is and the index table is flattened on the device
+	const size_t geometrySize = sizeof(DqnV4) * (size_t)numVertexes, textureSize = sizeof(DqnV3) * (size_t)numTexUV;
+	const size_t normalSize = sizeof(DqnV3) * (size_t)numNormals, faceSize = sizeof(DTRMeshFace) * (size_t)numFaces;
+	u8 *block = (u8 *)calloc(1, geometrySize + textureSize + normalSize + faceSize + 36 * (size_t)numFaces);
+	u8 *at    = block;
 	DTRMesh mesh     = {};
-	mesh.vertexes    = (DqnV4 *)vertexes;
+	mesh.vertexes    = (DqnV4 *)at;
+	at += geometrySize;
+	mesh.texUV = (DqnV3 *)at;
+	at += textureSize;
+	mesh.normals = (DqnV3 *)at;
+	at += normalSize;
+	mesh.faces = (DTRMeshFace *)at;
+	at += faceSize;
+	memcpy(mesh.vertexes, vertexes, geometrySize);
+	memcpy(mesh.texUV, texUV, textureSize);
+	memcpy(mesh.normals, normals, normalSize);
 	mesh.numVertexes = (u32)numVertexes;
-	mesh.texUV       = (DqnV3 *)texUV;
 	mesh.numTexUV    = (u32)numTexUV;
-	mesh.normals     = (DqnV3 *)normals;
 	mesh.numNormals  = (u32)numNormals;
 	mesh.numFaces    = (u32)numFaces;
-	mesh.faces       = (DTRMeshFace *)calloc((size_t)numFaces, sizeof(DTRMeshFace));
 	for (int i = 0; i < numFaces; i++)
 	{
-		i32 *f                       = (i32 *)(faces + 9 * (size_t)i);
+		memcpy(at, faces + 9 * (size_t)i, 36);
+		i32 *f                       = (i32 *)at;
+		at += 36;
 		mesh.faces[i].vertexIndex    = f + 0;
 		mesh.faces[i].numVertexIndex = 3;
 		mesh.faces[i].texIndex       = f + 3;
@@ -199,9 +215,8 @@ void dtro_mesh(dtro_ctx *c, const float *vertexes, int numVertexes, const float 
 	light.color  = DqnV4_4f(lightColor[0], lightColor[1], lightColor[2], lightColor[3]);
 	DTRRenderB200_Mesh(c->ctx, c->ctx.jobQueue, &mesh, light, DqnV3_3f(pos[0], pos[1], pos[2]), MakeTransform(transform));
 	// this harness rebuilds the DTRMesh per call, so drop the cache entry keyed by its stack address
-	DTRB200Binding *b = DTRB200_Bind(&c->rb);
-	if (b) b->meshes.erase(&mesh);
-	free(mesh.faces);
+	DTRRenderB200_Invalidate(&mesh);
+	free(block);
 }
 
 void dtro_rectangle(dtro_ctx *c, const float min[2], const float max[2], const float color[4], const float transform[7])

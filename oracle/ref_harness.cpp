@@ -247,4 +247,9 @@ void dtro_premultiply_bitmap(uint32_t *pixels, int count)
 	}
 }
 
+// The reference's own number parsers (dqn.h:3335-3454), which DTRAsset_LoadWavefrontObj feeds every
+// vertex and index through: exported so that the host-side .obj loader's restatement can be pinned.
+float   dtro_ref_strtof32(const char *buf, int len) { return Dqn_StrToF32(buf, len); }
+int64_t dtro_ref_strtoi64(const char *buf, int len) { return Dqn_StrToI64(buf, len); }
+
 } // extern "C"

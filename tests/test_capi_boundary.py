@@ -64,3 +64,36 @@ def test_create_fails_loudly_without_a_gpu(built):
     assert lib.dtr_b200_create(0, 64, 64, 1, ctypes.byref(h)) == -2  # DTR_B200_ERR_CUDA
     assert lib.dtr_b200_last_error(None)
     assert lib.dtr_b200_create(0, 0, 64, 1, ctypes.byref(h)) == -1   # DTR_B200_ERR_ARG comes first
+
+
+def test_band_partition_of_the_c_abi_matches_the_python_mirror(built):
+    """dtr_b200_band_rows is THE partition (dtr_b200_gather_bands uses it); multigpu.band_rows must agree."""
+    from dtrenderer_b200 import api, multigpu
+    lib = api.load_library()
+    th = lib.dtr_b200_tile_height()
+    assert th in (24, 32)
+    y0, y1 = ctypes.c_int(), ctypes.c_int()
+    for h in (1, 31, 32, 33, 600, 1080, 2160):
+        for world in (1, 2, 3, 4, 8):
+            rows = []
+            for r in range(world):
+                assert lib.dtr_b200_band_rows(h, world, r, ctypes.byref(y0), ctypes.byref(y1)) == 0
+                assert (y0.value, y1.value) == multigpu.band_rows(h, world, r, th)
+                rows.append((y0.value, y1.value))
+            assert rows[0][0] == 0 and rows[-1][1] == h and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+    assert lib.dtr_b200_band_rows(1080, 2, 2, ctypes.byref(y0), ctypes.byref(y1)) == -1
+
+
+def test_band_exchange_entry_points_fail_loudly_without_a_context(built):
+    from dtrenderer_b200 import api
+    lib = api.load_library()
+    assert lib.dtr_b200_gather_bands(None, 0, 0) == -1
+    assert lib.dtr_b200_band_barrier(None) == -1
+    assert lib.dtr_b200_band_comm_init(None, None, 2, 0) == -1
+
+
+def test_library_has_no_link_time_nccl_dependency(built):
+    """NCCL is bound with dlopen at the first band call; a host without NCCL can still load the module."""
+    from dtrenderer_b200 import api
+    ldd = subprocess.run(["ldd", api.LIB_PATH], capture_output=True, text=True).stdout
+    assert "nccl" not in ldd
