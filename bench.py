@@ -371,7 +371,11 @@ def measure_views(env, name, views, steps, warmup, e2e_steps, with_e2e):
     st = r.stats()
     shaded_per_step, tris_per_step = st["setPixels"], st["triangles"]
     tex_bytes = 4 * min(shaded_per_step // B, s["tex"] * s["tex"]) if s["textured"] else 0
-    alg_bytes = B * (8 * w * h + 156 * TRIS_PER_FRAME + tex_bytes)  # SURVEY.md §8(d); overlay quads not counted
+    # one 8-byte store per pixel + 156 B per triangle + the texels touched; a blit's
+    # destination pixels count once more as 8 B (read + write) -- the overlay quads of configs[2]
+    blit_px = sum(max(0, min(int(kw["mx"][0]), w) - max(int(kw["mn"][0]), 0)) * max(0, min(int(kw["mx"][1]), h) - max(int(kw["mn"][1]), 0))
+                  for kw in scene.overlays)
+    alg_bytes = B * (8 * w * h + 156 * TRIS_PER_FRAME + tex_bytes + 8 * blit_px)
 
     # ---- device-resident throughput: replay() ------------------------------------------------
     for _ in range(max(warmup, 3)):
@@ -475,18 +479,6 @@ def measure_views(env, name, views, steps, warmup, e2e_steps, with_e2e):
         if not np.array_equal(host[last_half, k].numpy().view(np.uint32), o.color()):
             raise SystemExit(f"bench.py: PARITY FAILURE {name}: e2e readback of view {view0 + (nsub - 1) * sub + k} differs")
     o.close()
-    # platform ceiling of the readback alone: the same bytes, all ranks at once, no rendering
-    e0c, e1c = env.events()
-    dcol = torch.empty((sub, h, w), dtype=torch.int32, device="cuda")
-    host[0].copy_(dcol, non_blocking=True)
-    env.barrier()
-    e0c.record(env.stream)
-    for i in range(2 * nsub):
-        host[i & 1].copy_(dcol, non_blocking=True)
-    e1c.record(env.stream)
-    env.barrier()
-    d2h_ms = env.max_over_ranks(e0c.elapsed_time(e1c)) / 2
-    del dcol
     # the same loop with the on-device 24-bit DIB encode (3 bytes per pixel over PCIe); reported beside
     # `e2e`, which stays the u32 DTRRenderBuffer layout
     pitch = r.bgr24_pitch()
@@ -499,6 +491,19 @@ def measure_views(env, name, views, steps, warmup, e2e_steps, with_e2e):
                                  host[last_half].view(torch.uint8).reshape(sub, h, w, 4)[..., :3]))
     if not packed_ok:
         raise SystemExit(f"bench.py: PARITY FAILURE {name}: 24-bit readback differs from the u32 readback")
+    # platform ceiling of the readback alone: the same bytes, all ranks at once, no rendering
+    # (last: it overwrites the pinned buffers the comparisons above read)
+    e0c, e1c = env.events()
+    dcol = torch.empty((sub, h, w), dtype=torch.int32, device="cuda")
+    host[0].copy_(dcol, non_blocking=True)
+    env.barrier()
+    e0c.record(env.stream)
+    for i in range(2 * nsub):
+        host[i & 1].copy_(dcol, non_blocking=True)
+    e1c.record(env.stream)
+    env.barrier()
+    d2h_ms = env.max_over_ranks(e0c.elapsed_time(e1c)) / 2
+    del dcol
     out["e2e"] = {"value": world * shaded_per_step / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
                   "h2d_bytes_per_step": upload[0] * nsub, "d2h_bytes_per_step": B * 4 * w * h,
                   "ms_per_step": e2e_ms, "frames_per_s": world * B / (e2e_ms * 1e-3), "steps": e2e_steps,

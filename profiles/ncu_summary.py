@@ -2,7 +2,7 @@
 """Turn one `ncu --set full` report into the summaries kept under profiles/:
    <tag>_raster_details.txt  (ncu --page details), <tag>_raster_raw.json (selected raw metrics),
    <tag>_raster_lines.txt (per-source-line shares, ncu_lines.py) and the dram traffic per launch.
-usage: ncu_summary.py gpurun_out/X.ncu-rep <tag> [workload-key-for-raster_traffic.json]"""
+usage: ncu_summary.py gpurun_out/X.ncu-rep <tag> [workload-key-for-raster_traffic.json views-in-the-captured-launch]"""
 import csv
 import io
 import json
@@ -12,6 +12,7 @@ import sys
 
 rep, tag = sys.argv[1], sys.argv[2]
 key = sys.argv[3] if len(sys.argv) > 3 else None
+views = int(sys.argv[4]) if len(sys.argv) > 4 else 64
 here = os.path.dirname(os.path.abspath(__file__))
 
 details = subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout
@@ -43,9 +44,10 @@ print("dram traffic per launch:", traffic)
 if key:
     p = os.path.join(here, "raster_traffic.json")
     t = json.load(open(p)) if os.path.exists(p) else {}
-    t[key] = traffic
-    t["source"] = (f"profiles/{tag}_raster_raw.json: dram__bytes_read.sum + dram__bytes_write.sum of one raster_kernel "
-                   "launch, ncu --set full")
+    t[key] = {"bytes_per_frame": int(traffic / views),
+              "source": (f"profiles/{tag}_raster_raw.json (ncu --set full, one raster launch of {views} views: "
+                         f"dram read {to_bytes(out['dram__bytes_read.sum']) / 1e6:.1f} MB + write "
+                         f"{to_bytes(out['dram__bytes_write.sum']) / 1e6:.1f} MB)")}
     json.dump(t, open(p, "w"), indent=1)
 
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout

@@ -31,15 +31,17 @@ def _same(col, z, o):
 
 
 def test_uv_exactly_one_stays_inside_the_texture_allocation(built):
-    """v == 1 indexes texel row h like the reference does (DTRendererRender.cpp:1196-1203).  The
-    reference reads whatever follows its bitmap; the oracle is handed a bitmap followed by zeros, which
-    is what the device allocation's spare row holds, so the frames must agree bit for bit."""
+    """v == 1 indexes texel row h (DTRendererRender.cpp:1196-1203).  The reference build asserts there
+    (`texelYf < dim.h`, DTR_DEBUG 1) and would otherwise read whatever follows its bitmap, so this case
+    is checked against the C restatement, which has no assert: it is handed a bitmap followed by zeros,
+    which is what the device allocation's spare row holds, so the frames must agree bit for bit."""
     w, h, tw, th = 200, 160, 16, 8
     rng = np.random.default_rng(5)
     buf = np.zeros((th + 2, tw, 4), np.uint8)
     buf[:th] = scenes.random_texture(tw, th, 3, opaque=False)
     tex = buf[:th]  # contiguous view: rows th, th+1 of buf (zeros) follow it in memory
-    o, r = _oracle(w, h), _renderer(w, h)
+    from oracle import dtro
+    o, r = dtro.Oracle(w, h, "port"), _renderer(w, h)
     r.begin_frame(0)
     for t in (o, r):
         t.clear((0.2, 0.3, 0.4))

@@ -2,7 +2,7 @@
 TAG=${1:-r02x}
 O=gpurun_out
 mkdir -p $O
-python -m pytest tests -m gpu -x -q -rs > $O/${TAG}_pytest.log 2>&1; tail -15 $O/${TAG}_pytest.log
+python -X faulthandler -m pytest tests -m gpu -q -rs > $O/${TAG}_pytest.log 2>&1; tail -15 $O/${TAG}_pytest.log
 python bench.py --steps 20 --warmup 5 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "bench rc=$?"; tail -5 $O/${TAG}_bench.err
 NG=$(nvidia-smi -L | wc -l)
 if [ "$NG" -ge 2 ]; then
@@ -20,3 +20,4 @@ for f in sorted(glob.glob("gpurun_out/%s_bench*.json" % os.environ.get("TAG", sy
     for o in d.get("other_workloads", []):
         print("   ", o["workload"], "value %.1f ms/step %.3f frac %.3f parity %s" % (o["value"], o["ms_per_step"], o["roofline"]["frac"], o.get("parity_checked")))
 PY
+if [ -n "$VARIANTS" ]; then bash tools/ab_variants.sh $VARIANTS; fi
