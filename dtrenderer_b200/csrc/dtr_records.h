@@ -21,7 +21,7 @@ constexpr int TILE_W      = 64;
 #ifndef DTR_TILE_H
 #define DTR_TILE_H 32
 #endif
-constexpr int TILE_H      = DTR_TILE_H; // 32, or 24 (divides 1080 and 2160; 6 CTAs per SM fit)
+constexpr int TILE_H      = DTR_TILE_H; // 32 (the only height the round-2 raster kernel supports, see its static_assert)
 constexpr int REGION_W    = 32;
 constexpr int REGION_H    = TILE_H;
 constexpr int SUB_W       = 8;
