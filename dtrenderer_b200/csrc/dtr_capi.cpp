@@ -455,6 +455,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	R.setPixels  = c->dSetPixels;
 	R.workCounter    = (uint32_t *)(S.counters + 3);
 	R.numBusy        = (const uint32_t *)(S.counters + 4);
+	R.listTotal      = S.counters + 1;
 	R.zeroBase       = dSegCount;
 	R.zeroWords      = zeroBytes / sizeof(uint32_t);
 	R.anyTextured    = c->last.anyTextured ? 1u : 0u;

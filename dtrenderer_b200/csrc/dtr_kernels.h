@@ -87,6 +87,7 @@ struct RasterParams
 	unsigned long long *setPixels;
 	uint32_t           *workCounter;    // zeroed by scan_kernel; items handed out by atomicAdd
 	const uint32_t     *numBusy;        // written by scan_kernel
+	const unsigned long long *listTotal; // (primitive, tile) pairs of the pass, written by scan_kernel
 	uint32_t           *zeroBase;       // counters + look-back words to clear for the next pass (may be null)
 	size_t              zeroWords;
 	uint32_t            anyTextured;    // some primitive of this pass samples a texture: raster_tex_kernel
