@@ -395,6 +395,7 @@ def measure_views(env, name, views, steps, warmup, e2e_steps, with_e2e):
     ms_step = env.max_over_ranks(e0.elapsed_time(e1)) / steps
     stage, runs = r.stage_ms()
     env.launches += r.stats()["kernelLaunches"]
+    deferred = r.last_pass_deferred()
     # parity of what the TIMED path left in the frames: first, middle and last view of this rank
     pairs = sorted({(0, view0), (B // 2, view0 + B // 2), (B - 1, view0 + B - 1)})
     checked = check_view_frames(r, scene, pairs)
@@ -421,7 +422,9 @@ def measure_views(env, name, views, steps, warmup, e2e_steps, with_e2e):
         "parity_checked": True,
         "parity": f"{checked} frames per rank of the timed replay (first, middle, last view) bit-equal in colour and depth "
                   f"to the {oracle_kind()} oracle at {w}x{h}",
-        "roofline": {"bound": "hbm", "kernel": "raster_tex_kernel" if s["textured"] else "raster_kernel",
+        "roofline": {"bound": "hbm", "kernel": ("raster_vis_kernel + resolve_kernel (deferred raster stage: every primitive an opaque "
+                                                "triangle; both kernels inside the timed interval)") if deferred
+                     else ("raster_tex_kernel" if s["textured"] else "raster_kernel"),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": tr_frame * B if tr_frame else None,
                      "traffic_source": (tr_src + " (a committed capture scaled to this batch, not measured in this run)") if tr_src else None,
@@ -636,6 +639,7 @@ def measure_fill(env, name, n_override, steps, warmup, e2e_steps, gather, with_e
     ms_step = env.max_over_ranks(e0.elapsed_time(e1)) / steps
     stage, runs = r.stage_ms()
     env.launches += r.stats()["kernelLaunches"]
+    deferred = r.last_pass_deferred()
     r.set_profiling(False)
 
     # ---- parity of the frame the timed steps left in rank 0's HBM ---------------------------
@@ -677,7 +681,8 @@ def measure_fill(env, name, n_override, steps, warmup, e2e_steps, gather, with_e
             else "grouped ncclSend/ncclRecv gather (dtr_b200_gather_bands)")) if world > 1 else "single GPU, whole frame",
         "exchange_bytes_per_step_into_rank0": 8 * w * (h - multigpu.band_rows(h, world, 0, r.tile_height())[1]) if world > 1 else 0,
         "parity_checked": True, "parity": "; ".join(parity),
-        "roofline": {"bound": "hbm", "kernel": "raster_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "raster_vis_kernel + resolve_kernel" if deferred else "raster_kernel",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": raster_ms,
                      "stage_ms_per_step": {k: v / max(runs, 1) for k, v in stage.items()},

@@ -95,6 +95,7 @@ SYMBOLS = [
     ("dtr_b200_frame_device_ptrs", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     ("dtr_b200_get_stats", C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     ("dtr_b200_reset_stats", C.c_int, [C.c_void_p]),
+    ("dtr_b200_last_pass_deferred", C.c_int, [C.c_void_p]),
     ("dtr_b200_set_profiling", C.c_int, [C.c_void_p, C.c_int]),
     ("dtr_b200_get_stage_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float * 4), C.POINTER(C.c_int)]),
     ("dtr_b200_reset_stage_ms", C.c_int, [C.c_void_p]),
@@ -398,6 +399,10 @@ class Renderer:
         s = Stats()
         self._ck(self.lib.dtr_b200_get_stats(self.ctx, C.byref(s)))
         return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
+
+    def last_pass_deferred(self):
+        """True when the last flush / replay used the deferred raster stage (visibility + resolve kernels)."""
+        return bool(self.lib.dtr_b200_last_pass_deferred(self.ctx))
 
     def reset_stats(self):
         self._ck(self.lib.dtr_b200_reset_stats(self.ctx))

@@ -55,6 +55,7 @@ struct RecItem
 	uint32_t order;      // submission order (stable sort key)
 	size_t   payload[3]; // byte offsets into the payload buffer (valid where relocate[j])
 	bool     relocate[3];
+	bool     opaque;     // triangles whose every fragment has alpha 1 (colour alpha 1, no texture or an opaque one)
 };
 
 struct FrameHost
@@ -114,6 +115,7 @@ struct dtr_b200_ctx
 	std::vector<MeshAsset> meshes;
 	std::vector<TexDesc>   textures;
 	std::vector<uint8_t>   texIsWhite; // every texel 0xFFFFFFFF: sampling multiplies by exactly 1.0f
+	std::vector<uint8_t>   texIsOpaque; // every texel has alpha 255: a textured fragment keeps its colour's alpha
 	DevBuf                 dTextures;
 
 	DevBuf dCmd, dPayload;
@@ -150,6 +152,7 @@ struct dtr_b200_ctx
 		uint32_t numActive = 0, numItems = 0, numPrims = 0, maxFramePrims = 0;
 		uint64_t listTotal = 0, triangles = 0;
 		bool     anyTextured = false; // some triangle item of the flush samples a (non-white) texture
+		bool     deferred    = false; // every primitive an opaque triangle, every frame cleared on chip: visibility + resolve
 		Geometry g{};
 	} last;
 
@@ -278,6 +281,8 @@ int record_tris(dtr_b200_ctx *c, int n, const float *p, const float *color, cons
 	r.payload[2]     = offUV;
 	r.relocate[2]    = (uv != nullptr);
 	r.item.texId     = (texId >= 0 && c->texIsWhite[texId]) ? -1 : texId;
+	r.opaque         = r.item.texId < 0 || c->texIsOpaque[r.item.texId];
+	for (int i = 0; i < n && r.opaque; i++) r.opaque = color[4 * (size_t)i + 3] == 1.0f;
 	r.item.lightMode = DTR_B200_SHADE_FULLBRIGHT; // NullRenderLightInternal (:1352-1356)
 	Basis2 b         = make_basis(t->rotation, t->scale[0], t->scale[1]);
 	r.item.xAxis[0] = b.xAxis[0]; r.item.xAxis[1] = b.xAxis[1];
@@ -463,8 +468,16 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	R.smallTilesMin  = 0;
 	R.g          = g;
 	if ((rc = mark(c, c->stream))) return rc;
-	launch_raster(R, c->limits, c->stream);
-	c->launches++;
+	if (c->last.deferred)
+	{
+		launch_raster_deferred(R, c->limits, c->stream);
+		c->launches += 2;
+	}
+	else
+	{
+		launch_raster(R, c->limits, c->stream);
+		c->launches++;
+	}
 	if ((rc = mark(c, c->stream))) return rc;
 	CU(cudaEventRecord(S.rasterDone, c->stream));
 	S.rasterPending = true;
@@ -574,6 +587,19 @@ int do_flush(dtr_b200_ctx *c)
 
 	c->last.anyTextured = false;
 	for (uint32_t i = 0; i < numItems; i++) c->last.anyTextured = c->last.anyTextured || (it[i].type != ITEM_RAW && it[i].texId >= 0);
+	// Deferred pass (dtr_deferred.cuh): only when nothing can ever be blended -- every primitive an opaque
+	// triangle, every frame starting from an on-chip clear -- and the frames are this context's own planes
+	// (the resolve kernel reads what the visibility kernel wrote; over NVLink that would be a read-back).
+	{
+		static const bool allow = [] {
+			const char *e = getenv("DTR_B200_DEFER"); // "0": always the single-kernel raster stage
+			return !(e && e[0] == '0');
+		}();
+		bool deferred = allow && numItems > 0 && c->outColor == c->dColor;
+		for (uint32_t s2 = 0; s2 < numActive && deferred; s2++) deferred = (fs[s2].init & FI_COLOR_CLEAR) != 0;
+		for (uint32_t i = 0; i < numItems && deferred; i++) deferred = c->rec[i].item.type != ITEM_RAW && c->rec[i].opaque;
+		c->last.deferred = deferred;
+	}
 	uint32_t maxFramePrims = 0;
 	for (uint32_t s2 = 0; s2 < numActive; s2++) maxFramePrims = std::max(maxFramePrims, fs[s2].primEnd - fs[s2].primBegin);
 	rc = run_pipeline(c, numActive, numItems, (uint32_t)prim, maxFramePrims, false);
@@ -773,6 +799,9 @@ int dtr_b200_upload_texture(dtr_b200_ctx *c, const uint8_t *texels, int width, i
 			for (size_t i = 0; i < bytes && white; i++) white = (texels[i] == 0xFF);
 		}
 		c->texIsWhite.push_back(white ? 1 : 0);
+		bool opaque = true;
+		for (size_t i = 3; i < bytes && opaque; i += 4) opaque = (texels[i] == 0xFF);
+		c->texIsOpaque.push_back(opaque ? 1 : 0);
 	}
 	CU(cudaStreamSynchronize(c->stream)); // the old table may be in use
 	int rc = ensure_dev(c, c->dTextures, sizeof(TexDesc) * std::max<size_t>(c->textures.capacity(), 16));
@@ -797,6 +826,9 @@ int dtr_b200_update_texture(dtr_b200_ctx *c, int texId, const uint8_t *texels)
 	bool white = true;
 	for (size_t i = 0; i < count * 4 && white; i++) white = (texels[i] == 0xFF);
 	c->texIsWhite[texId] = white ? 1 : 0;
+	bool opaque = true;
+	for (size_t i = 3; i < count * 4 && opaque; i += 4) opaque = (texels[i] == 0xFF);
+	c->texIsOpaque[texId] = opaque ? 1 : 0;
 	c->last.valid        = false; // a replay would keep the old "textured" decision
 	return DTR_B200_OK;
 }
@@ -1320,6 +1352,8 @@ int dtr_b200_get_stats(dtr_b200_ctx *c, dtr_b200_stats *out)
 	return DTR_B200_OK;
 }
 
+int dtr_b200_last_pass_deferred(const dtr_b200_ctx *c) { return (c && c->last.valid && c->last.deferred) ? 1 : 0; }
+
 int dtr_b200_selftest(dtr_b200_ctx *c, uint64_t *mismatches)
 {
 	if (!c || !mismatches) return DTR_B200_ERR_ARG;
@@ -1458,6 +1492,7 @@ int dtr_b200_mesh_views(dtr_b200_ctx *c, int meshId, const dtr_b200_light *light
 		RecItem &r = new_item(c, ITEM_MESH, (uint32_t)(firstFrame + v), m.numFaces);
 		// DTRRender_Mesh always samples mesh->tex (:1563-1564); an all-white one is a no-op
 		r.item.texId     = (m.texId >= 0 && c->texIsWhite[m.texId]) ? -1 : m.texId;
+		r.opaque         = light->color[3] == 1.0f && (r.item.texId < 0 || c->texIsOpaque[r.item.texId]);
 		r.item.lightMode = (uint32_t)light->mode;
 		r.item.ptr[0]    = (uint64_t)m.vertexes;
 		r.item.ptr[1]    = (uint64_t)m.texUV;

@@ -102,6 +102,7 @@ struct LaunchLimits
 {
 	int sms          = 148;
 	int residentCtas = 148; // raster CTAs resident on the whole device (sms x CTAs per SM)
+	int residentCtasVis = 148; // ... of the deferred pass's visibility kernel
 };
 LaunchLimits query_launch_limits(int device);
 void         launch_init_tables(cudaStream_t s); // per-device lookup tables of the raster kernel (once per context)
@@ -120,6 +121,15 @@ struct FlattenParams
 };
 void launch_flatten_faces(const FlattenParams &P, cudaStream_t s);
 
+struct ResolveParams
+{
+	uint32_t         *color;   // [F][H][W]: finished colours and pending primitive tags
+	const PrimRecord *prims;
+	const uint4      *order;   // tile descriptors in work order: the busy tiles are the first *numBusy
+	const uint32_t   *numBusy;
+	Geometry          g;
+};
+
 void launch_setup(const SetupParams &P, cudaStream_t s);
 // Scans the tile counts (-> totals[0]); the offsets array gets one extra trailing entry holding the
 // total.  Also zeroes the raster work counter and writes the work order.
@@ -128,6 +138,8 @@ void launch_tile_sum(const TileSumParams &P, cudaStream_t s);
 void launch_selftest_sqrt(unsigned long long *mismatches, cudaStream_t s);
 void launch_bin(const BinParams &P, const LaunchLimits &L, cudaStream_t s);
 void launch_raster(const RasterParams &P, const LaunchLimits &L, cudaStream_t s);
+// the deferred variant of the raster stage (dtr_deferred.cuh): raster_vis_kernel + resolve_kernel
+void launch_raster_deferred(const RasterParams &P, const LaunchLimits &L, cudaStream_t s);
 void launch_premultiply(uint32_t *pixels, size_t count, cudaStream_t s);
 void launch_pack_bgr24(const uint32_t *color, uint32_t *out, int width, size_t rows, int pitchWords, cudaStream_t s);
 

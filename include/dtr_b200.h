@@ -252,6 +252,10 @@ int dtr_b200_band_barrier(dtr_b200_ctx *ctx);
  * (NCCL / peer access / torch views). */
 int dtr_b200_frame_device_ptrs(dtr_b200_ctx *ctx, int frame, void **color, void **z);
 int dtr_b200_get_stats(dtr_b200_ctx *ctx, dtr_b200_stats *out); /* syncs */
+/* 1 when the last flush / replay ran its raster stage as the deferred pair of kernels (visibility +
+ * resolve: every primitive an opaque triangle, every frame cleared on chip; DTR_B200_DEFER=0 in the
+ * environment turns the variant off), 0 for the single raster kernel.  Results are identical. */
+int dtr_b200_last_pass_deferred(const dtr_b200_ctx *ctx);
 int dtr_b200_reset_stats(dtr_b200_ctx *ctx);
 /* Per-stage device timing with CUDA events on the context's stream (the ncu/nsys replacement of
  * the reference's rdtsc region counters, DTRendererDebug.h:42-78).  While enabled, every
