@@ -539,30 +539,37 @@ __global__ void __launch_bounds__(128, VIS_CTAS_PER_SM) raster_vis_kernel(Raster
 // the tile, row-major: a warp reads and writes whole 128-byte row segments.
 __global__ void __launch_bounds__(256) resolve_kernel(ResolveParams R)
 {
+	constexpr int  PER_THREAD = TILE_W * TILE_H / 256;
 	const uint32_t nBusy = *R.numBusy;
 	const size_t   plane = (size_t)R.g.width * R.g.height;
+	const int      px0 = (int)threadIdx.x & (TILE_W - 1), py0 = (int)threadIdx.x / TILE_W; // pixel of the first of the thread's rows
 	for (uint32_t slot = blockIdx.x; slot < nBusy; slot += gridDim.x)
 	{
 		const uint4 d0 = __ldg(R.order + 2 * slot), d1 = __ldg(R.order + 2 * slot + 1);
-		const int   tx = (int)(d1.z & 0xFFFFu), ty = (int)(d1.z >> 16);
-		uint32_t   *gC = R.color + plane * d0.w;
-#pragma unroll 2
-		for (int k = 0; k < TILE_W * TILE_H / 256; k++)
+		const int   x = (int)(d1.z & 0xFFFFu) * TILE_W + px0, yTop = (int)(d1.z >> 16) * TILE_H + py0;
+		uint32_t   *col = R.color + plane * d0.w + (size_t)yTop * R.g.width + x;
+		// all of the thread's tags first: eight independent loads in flight (the tags come from DRAM: the
+		// visibility kernel wrote a gigabyte of frames since it stored them)
+		uint32_t v[PER_THREAD];
+#pragma unroll
+		for (int k = 0; k < PER_THREAD; k++)
 		{
-			const int p = (int)threadIdx.x + 256 * k;
-			const int x = tx * TILE_W + (p & (TILE_W - 1)), y = ty * TILE_H + (p / TILE_W);
-			if (x >= R.g.width || y >= R.g.height) continue;
-			uint32_t      *px = gC + (size_t)y * R.g.width + x;
-			const uint32_t v  = *px;
-			if (!(v & VIS_PENDING)) continue;
-			const uint4 *rec = reinterpret_cast<const uint4 *>(R.prims + (v & ~VIS_PENDING));
+			const int y = yTop + k * (256 / TILE_W);
+			v[k] = (x < R.g.width && y < R.g.height) ? __ldcs(col + (size_t)k * (256 / TILE_W) * R.g.width) : 0u;
+		}
+#pragma unroll 2
+		for (int k = 0; k < PER_THREAD; k++)
+		{
+			if (!(v[k] & VIS_PENDING)) continue;
+			const int    y   = yTop + k * (256 / TILE_W);
+			const uint4 *rec = reinterpret_cast<const uint4 *>(R.prims + (v[k] & ~VIS_PENDING));
 			const uint4  q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
 			// the int32 edge functions at this pixel: bbox-origin value + steps (exact, see setup_kernel)
 			const int rx = x - (int)(q0.z & 0xFFFF), ry = y - (int)(q0.z >> 16);
 			const int E1 = (int)q1.x + rx * (int)q1.w + ry * (int)q2.z;
 			const int E2 = (int)q1.y + rx * (int)q2.x + ry * (int)q2.w;
 			const int E3 = (int)q1.z + rx * (int)q2.y + ry * (int)q3.x;
-			frame_store_u32(px, shade_opaque_from_record(rec, (float)E1, (float)E2, (float)E3));
+			frame_store_u32(col + (size_t)k * (256 / TILE_W) * R.g.width, shade_opaque_from_record(rec, (float)E1, (float)E2, (float)E3));
 		}
 	}
 }
