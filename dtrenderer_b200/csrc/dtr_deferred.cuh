@@ -537,12 +537,31 @@ __global__ void __launch_bounds__(128, VIS_CTAS_PER_SM) raster_vis_kernel(Raster
 // Resolve: every pixel of the tiles that have primitives; a pixel that still carries a tag is shaded
 // from its triangle's record.  One CTA per busy tile (grid-stride), thread t takes pixels t + 256 k of
 // the tile, row-major: a warp reads and writes whole 128-byte row segments.
-__global__ void __launch_bounds__(256) resolve_kernel(ResolveParams R)
+#ifndef DTR_RESOLVE_MIN_CTAS
+#define DTR_RESOLVE_MIN_CTAS 8 // 32 registers: all 64 warps of an SM resident
+#endif
+#ifndef DTR_RESOLVE_UNROLL
+#define DTR_RESOLVE_UNROLL 8 // (2: -1 %; the tags then live in local memory)
+#endif
+#ifndef DTR_RESOLVE_BLOCKS
+#define DTR_RESOLVE_BLOCKS 0
+#endif
+#ifndef DTR_RESOLVE_PREFETCH
+#define DTR_RESOLVE_PREFETCH 0
+#endif
+#define DTR_RESOLVE_PRAGMA_(x) _Pragma(#x)
+#define DTR_RESOLVE_UNROLL_PRAGMA(n) DTR_RESOLVE_PRAGMA_(unroll n)
+__global__ void __launch_bounds__(256, DTR_RESOLVE_MIN_CTAS) resolve_kernel(ResolveParams R)
 {
 	constexpr int  PER_THREAD = TILE_W * TILE_H / 256;
 	const uint32_t nBusy = *R.numBusy;
 	const size_t   plane = (size_t)R.g.width * R.g.height;
+#if DTR_RESOLVE_BLOCKS
+	// a warp takes an 8x4 block of pixels (four 32-byte row segments): fewer distinct triangles per warp
+	const int      px0 = ((int)threadIdx.x >> 5) * 8 + ((int)threadIdx.x & 7), py0 = ((int)threadIdx.x >> 3) & 3;
+#else
 	const int      px0 = (int)threadIdx.x & (TILE_W - 1), py0 = (int)threadIdx.x / TILE_W; // pixel of the first of the thread's rows
+#endif
 	for (uint32_t slot = blockIdx.x; slot < nBusy; slot += gridDim.x)
 	{
 		const uint4 d0 = __ldg(R.order + 2 * slot), d1 = __ldg(R.order + 2 * slot + 1);
@@ -557,7 +576,18 @@ __global__ void __launch_bounds__(256) resolve_kernel(ResolveParams R)
 			const int y = yTop + k * (256 / TILE_W);
 			v[k] = (x < R.g.width && y < R.g.height) ? __ldcs(col + (size_t)k * (256 / TILE_W) * R.g.width) : 0u;
 		}
-#pragma unroll 2
+#if DTR_RESOLVE_PREFETCH
+		// the records the thread is going to read, on their way into L1 while the first pixel is shaded
+#pragma unroll
+		for (int k = 0; k < PER_THREAD; k++)
+			if (v[k] & VIS_PENDING)
+			{
+				const char *rp = reinterpret_cast<const char *>(R.prims + (v[k] & ~VIS_PENDING));
+				asm volatile("prefetch.global.L1 [%0];" ::"l"(rp));
+				asm volatile("prefetch.global.L1 [%0];" ::"l"(rp + 128));
+			}
+#endif
+		DTR_RESOLVE_UNROLL_PRAGMA(DTR_RESOLVE_UNROLL)
 		for (int k = 0; k < PER_THREAD; k++)
 		{
 			if (!(v[k] & VIS_PENDING)) continue;
