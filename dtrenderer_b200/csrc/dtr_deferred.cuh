@@ -34,6 +34,15 @@ struct VisSmem
 	uint4    sub[32];           // current triangle, per sub-block: {E1,E2,E3 at its origin as fp32 (exact), in-bbox pixel mask}
 };
 constexpr int      VIS_CTAS_PER_SM = 6;
+#ifndef DTR_VIS_LANE_COUNT
+#define DTR_VIS_LANE_COUNT 1 // SetPixel calls counted per lane (no vote in the coverage step), summed once per warp
+#endif
+#ifndef DTR_VIS_SMALL_WINDOWS
+#define DTR_VIS_SMALL_WINDOWS 0 // N > 0: exact triangles whose clipped bbox is at most N 8x4 windows skip the sub-block table (measured: 8 -> +2 %, 16 -> +6 % raster time; the table path culls hidden sub-blocks, this one cannot)
+#endif
+#ifndef DTR_VIS_EMPTY_SHIFT
+#define DTR_VIS_EMPTY_SHIFT 0 // (2: no gain) log2 of the untouched tiles per work item of a large launch
+#endif
 constexpr uint32_t VIS_PENDING     = 0x80000000u;
 
 // The reference's per-fragment arithmetic after the depth test for an OPAQUE fragment (SlowTriangle
@@ -178,7 +187,7 @@ __device__ __forceinline__ void process_region_vis(const RasterParams &P, VisSme
 #if DTR_SUB_ZCULL && DTR_REGION_ZCULL
 	int zsub = depth_key(-FLT_MAX);
 #endif
-	uint32_t       passes  = 0; // warp-uniform: fragments that passed the depth test = SetPixel calls
+	uint32_t       passes  = 0; // this LANE's fragments that passed the depth test = SetPixel calls (summed at the end of the kernel)
 	const uint32_t laneBit = 1u << lane;
 	const uint32_t zAddrLane = (uint32_t)__cvta_generic_to_shared(W.z + lane);
 	const uint32_t cAddrLane = (uint32_t)__cvta_generic_to_shared(W.c + lane);
@@ -232,7 +241,64 @@ __device__ __forceinline__ void process_region_vis(const RasterParams &P, VisSme
 			             :
 			             : "r"((uint32_t)pass), "r"(za), "f"(z), "r"(ca), "r"(tag)
 			             : "memory");
+#if DTR_VIS_LANE_COUNT
+			passes += pass ? 1u : 0u;
+#else
 			passes += __popc(__ballot_sync(FULL, pass));
+#endif
+		}
+	};
+
+	// exact triangle with a small bounding box: 8x4 WINDOWS laid from the bbox corner instead of the
+	// region's sub-block grid.  A 30-pixel mesh triangle (bbox ~8x8) is two windows but straddles five or
+	// six sub-blocks; and nothing is tabulated first (no classification, no table, no warp barriers).
+	// Lane (lx, ly) of a window is pixel (x0 + 8 wx + lx, y0 + 4 wy + ly): any 8x4 window of the linear
+	// sub-block layout falls on 32 different banks.  The edge functions are carried as fp32 and stepped
+	// by +8 dx / +4 dy: every value is an integer below 2^24 (the PF_EXACT bound covers the bbox grown by
+	// one window), so the sums are exact and the bits equal those of the table path.
+	auto raster_tri_small = [&](const uint4 g0, const uint4 g1, const uint4 g2, const uint4 g4, const int nwx, const int nwy) {
+		const int      x0 = g0.w & 0xFF, y0 = (g0.w >> 8) & 0xFF, x1 = (g0.w >> 16) & 0xFF, y1 = g0.w >> 24;
+		const float4   zp  = u2f4(g4); // 1/area, z1, z2-z1, z3-z1
+		const uint32_t tag = VIS_PENDING | g2.w;
+		const int      dx1 = (int)g1.x, dx2 = (int)g1.y, dx3 = (int)g1.z;
+		const int      dy1 = (int)g2.x, dy2 = (int)g2.y, dy3 = (int)g2.z;
+		const int      pxl = x0 + lx, pyl = y0 + ly; // this lane's pixel of the first window
+		float          r1 = (float)((int)g0.x + pxl * dx1 + pyl * dy1);
+		float          r2 = (float)((int)g0.y + pxl * dx2 + pyl * dy2);
+		float          r3 = (float)((int)g0.z + pxl * dx3 + pyl * dy3);
+		const float    sx1 = (float)(SUB_W * dx1), sx2 = (float)(SUB_W * dx2), sx3 = (float)(SUB_W * dx3);
+		const float    sy1 = (float)(SUB_H * dy1), sy2 = (float)(SUB_H * dy2), sy3 = (float)(SUB_H * dy3);
+		uint32_t       rowAddr = zAddrLane - 4u * (uint32_t)lane +
+		                   4u * (uint32_t)(((((pyl >> 2) * SUBS_X) + (pxl >> 3)) << 5) | ((pyl & 3) << 3) | (pxl & 7));
+		int            py = pyl;
+		__syncwarp(); // the triangle before touched these pixels through other lanes
+		for (int wy = 0; wy < nwy; wy++)
+		{
+			float      e1 = r1, e2 = r2, e3 = r3;
+			uint32_t   za = rowAddr;
+			int        px = pxl;
+			const bool rowIn = py < y1;
+			for (int wx = 0; wx < nwx; wx++)
+			{
+				const bool in = rowIn && (px < x1);
+				float      zOld = 0.0f;
+				asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q ld.shared.f32 %0, [%2];\n\t}" : "+f"(zOld) : "r"((uint32_t)in), "r"(za) : "memory");
+				const bool  covered = in && ((__float_as_int(e1) | __float_as_int(e2) | __float_as_int(e3)) >= 0);
+				const float bB = e2 * zp.x, bC = e3 * zp.x;
+				const float z  = (zp.y + (bB * zp.z)) + (bC * zp.w);
+				const bool  pass = covered & (z > zOld);
+				asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.shared.f32 [%1], %2;\n\t@q st.shared.u32 [%3], %4;\n\t}"
+				             :
+				             : "r"((uint32_t)pass), "r"(za), "f"(z), "r"(za - (uint32_t)(sizeof(uint32_t) * REGION_WORDS)), "r"(tag)
+				             : "memory");
+				passes += pass ? 1u : 0u;
+				e1 += sx1; e2 += sx2; e3 += sx3;
+				za += 32u * 4u; // the same pixel of the sub-block to the right
+				px += SUB_W;
+			}
+			r1 += sy1; r2 += sy2; r3 += sy3;
+			rowAddr += SUBS_X * 32u * 4u; // ... of the sub-block below
+			py += SUB_H;
 		}
 	};
 
@@ -272,8 +338,13 @@ __device__ __forceinline__ void process_region_vis(const RasterParams &P, VisSme
 			{
 				W.z[si] = z;
 				W.c[si] = shade_opaque_now(P.prims + pidx, e1, e2, e3);
+#if DTR_VIS_LANE_COUNT
+				passes++;
+#endif
 			}
+#if !DTR_VIS_LANE_COUNT
 			passes += __popc(__ballot_sync(FULL, pass));
+#endif
 		}
 		__syncwarp();
 	};
@@ -397,7 +468,16 @@ __device__ __forceinline__ void process_region_vis(const RasterParams &P, VisSme
 			for (int r = 0; r < ng; r++)
 			{
 				const uint4 g0r = W.geo[r * 5], g1 = W.geo[r * 5 + 1], g2 = W.geo[r * 5 + 2], g3 = W.geo[r * 5 + 3], g4 = W.geo[r * 5 + 4];
-				if (g1.w & PF_EXACT) raster_tri(g0r, g1, g2, g3, g4);
+				if (g1.w & PF_EXACT)
+				{
+#if DTR_VIS_SMALL_WINDOWS
+					const int bw = (int)((g0r.w >> 16) & 0xFF) - (int)(g0r.w & 0xFF), bh = (int)(g0r.w >> 24) - (int)((g0r.w >> 8) & 0xFF);
+					const int nwx = (bw + SUB_W - 1) / SUB_W, nwy = (bh + SUB_H - 1) / SUB_H;
+					if (nwx * nwy <= DTR_VIS_SMALL_WINDOWS) raster_tri_small(g0r, g1, g2, g4, nwx, nwy);
+					else
+#endif
+						raster_tri(g0r, g1, g2, g3, g4);
+				}
 				else raster_tri_replay(g3.w, g0r, g1, g2, g4);
 			}
 			__syncwarp();
@@ -406,7 +486,7 @@ __device__ __forceinline__ void process_region_vis(const RasterParams &P, VisSme
 	shaded += passes;
 
 	// ---- write the region back once (pending tags included: resolve_kernel finishes them) -----------
-	if (lane == 0) nextItem = atomicAdd(P.workCounter, 1u);
+	if (lane == 0) nextItem = atomicAdd(P.workCounter, 1u); // (the round trip runs behind the stores)
 	if (vec)
 	{
 		float4         *pz = reinterpret_cast<float4 *>(J.gZ + vOff);
@@ -463,9 +543,17 @@ __global__ void __launch_bounds__(128, VIS_CTAS_PER_SM) raster_vis_kernel(Raster
 #else
 	const uint32_t smallShift = 2u;
 #endif
-	const uint32_t itemsBusy = 2 * nBig + (nSmall << smallShift);
-	const uint32_t itemsMixed = itemsBusy + (uint32_t)(((unsigned long long)nEmpty * (100 - RASTER_TAIL_PERCENT)) / 100);
-	const uint32_t itemsTotal = itemsBusy + nEmpty;
+	// Untouched tiles are handed out FOUR per item when there are plenty: claiming an item and loading its
+	// tile entry is a dependent ~1.3 us, streaming a tile's clear values takes less (five tiles of six of
+	// the 1080p sphere views are untouched), so the four entries are loaded together and the claim is
+	// paid once.  (Claiming items ahead instead -- a ring of up to four claims per warp -- cost 12 %: the
+	// last busy regions then start late.)
+	const uint32_t warpsTotal  = gridDim.x * 4u;
+	const uint32_t emptyShift  = nEmpty >= 8u * warpsTotal ? (uint32_t)DTR_VIS_EMPTY_SHIFT : 0u;
+	const uint32_t emptyItems  = (nEmpty + (1u << emptyShift) - 1u) >> emptyShift;
+	const uint32_t itemsBusy   = 2 * nBig + (nSmall << smallShift);
+	const uint32_t itemsMixed  = itemsBusy + (uint32_t)(((unsigned long long)emptyItems * (100 - RASTER_TAIL_PERCENT)) / 100);
+	const uint32_t itemsTotal  = itemsBusy + emptyItems;
 	const unsigned long long ratio = itemsMixed ? ((((unsigned long long)itemsBusy << 32) + itemsMixed - 1) / itemsMixed) : 0ull;
 	uint32_t next = 0;
 	if (lane == 0) next = atomicAdd(P.workCounter, 1u);
@@ -473,46 +561,60 @@ __global__ void __launch_bounds__(128, VIS_CTAS_PER_SM) raster_vis_kernel(Raster
 	{
 		const uint32_t item = __shfl_sync(0xffffffffu, next, 0);
 		if (item >= itemsTotal) break;
-		uint32_t slot;
-		int      rx = 0, ry = 0, rows = 0;
+		bool     busy = false;
+		uint32_t b0 = itemsBusy;
+		if (item < itemsMixed)
 		{
-			bool     busy = false;
-			uint32_t b0 = itemsBusy;
-			if (item < itemsMixed)
-			{
-				b0   = (uint32_t)(((unsigned long long)item * ratio) >> 32);
-				busy = (uint32_t)(((unsigned long long)(item + 1u) * ratio) >> 32) > b0;
-			}
-			if (busy)
-			{
-				if (b0 < 2 * nBig)
+			b0   = (uint32_t)(((unsigned long long)item * ratio) >> 32);
+			busy = (uint32_t)(((unsigned long long)(item + 1u) * ratio) >> 32) > b0;
+		}
+		if (!busy)
+		{
+			if (lane == 0) next = atomicAdd(P.workCounter, 1u);
+			const uint32_t first = (item - b0) << emptyShift;
+			const uint32_t n     = min(1u << emptyShift, nEmpty - first);
+			uint32_t       fr[1 << DTR_VIS_EMPTY_SHIFT];
+			uint4          e1[1 << DTR_VIS_EMPTY_SHIFT];
+#pragma unroll
+			for (uint32_t k = 0; k < (1u << DTR_VIS_EMPTY_SHIFT); k++)
+				if (k < n)
 				{
-					slot = b0 >> 1;
-					rx   = (int)(b0 & 1) * REGION_W;
-					rows = REGION_H;
+					const uint32_t slot = numTiles - 1 - (first + k);
+					fr[k] = __ldg(&P.order[2 * slot].w);
+					e1[k] = __ldg(P.order + 2 * slot + 1);
 				}
-				else
+#pragma unroll
+			for (uint32_t k = 0; k < (1u << DTR_VIS_EMPTY_SHIFT); k++)
+				if (k < n)
 				{
-					const uint32_t k = b0 - 2 * nBig;
-					slot = nBig + (k >> smallShift);
-					rx   = (int)(k & 1) * REGION_W;
-					rows = REGION_H >> (smallShift - 1);
-					ry   = (int)((k >> 1) & ((1u << (smallShift - 1)) - 1u)) * rows;
+					const bool genZ = (e1[k].y & FI_Z_RESET) != 0, genC = (e1[k].y & FI_COLOR_CLEAR) != 0;
+					if (genZ || genC)
+						stream_empty_tile(P, (int)(e1[k].z & 0xFFFFu), (int)(e1[k].z >> 16), P.color + plane * fr[k], P.depth + plane * fr[k], genC,
+						                  genZ, e1[k].x, lane);
 				}
-			}
-			else slot = numTiles - 1 - (item - b0);
+			continue;
+		}
+		uint32_t slot;
+		int      rx, ry = 0, rows;
+		if (b0 < 2 * nBig)
+		{
+			slot = b0 >> 1;
+			rx   = (int)(b0 & 1) * REGION_W;
+			rows = REGION_H;
+		}
+		else
+		{
+			const uint32_t k = b0 - 2 * nBig;
+			slot = nBig + (k >> smallShift);
+			rx   = (int)(k & 1) * REGION_W;
+			rows = REGION_H >> (smallShift - 1);
+			ry   = (int)((k >> 1) & ((1u << (smallShift - 1)) - 1u)) * rows;
 		}
 		const uint4 d0 = __ldg(P.order + 2 * slot), d1 = __ldg(P.order + 2 * slot + 1);
 		const int   tx = (int)(d1.z & 0xFFFFu), ty = (int)(d1.z >> 16);
 		const bool  genZ = (d1.y & FI_Z_RESET) != 0, genC = (d1.y & FI_COLOR_CLEAR) != 0;
 		uint32_t   *gC = P.color + plane * d0.w;
 		float      *gZ = P.depth + plane * d0.w;
-		if (rows == 0)
-		{
-			if (lane == 0) next = atomicAdd(P.workCounter, 1u);
-			if (genZ || genC) stream_empty_tile(P, tx, ty, gC, gZ, genC, genZ, d1.x, lane);
-			continue;
-		}
 		RegionJob J;
 		J.gx   = tx * TILE_W + rx;
 		J.gy   = ty * TILE_H + ry;
@@ -531,6 +633,9 @@ __global__ void __launch_bounds__(128, VIS_CTAS_PER_SM) raster_vis_kernel(Raster
 		J.listOff     = d0.z;
 		process_region_vis(P, W, lane, J, shaded, next);
 	}
+#if DTR_VIS_LANE_COUNT
+	shaded = __reduce_add_sync(0xffffffffu, shaded);
+#endif
 	if (lane == 0 && shaded) atomicAdd(P.setPixels, (unsigned long long)shaded);
 }
 

@@ -241,3 +241,90 @@ def test_rotated_screen_size_triangles_at_4k(built):
     gpu_s = time.perf_counter() - t0
     _same(col, z, o)
     assert gpu_s < 2.0, f"the 4K replay frame took {gpu_s:.2f} s"
+
+
+# ---- the deferred raster stage (visibility + resolve kernels) ----------------------------------------
+_DEFER_SCRIPT = r"""
+import hashlib, sys, numpy as np
+sys.path.insert(0, %(root)r)
+from dtrenderer_b200 import api, scenes
+w, h = 517, 301   # not a multiple of the tile size or of 4: the scalar load/store paths
+r = api.Renderer(w, h, 2, 0)
+mesh, tex = scenes.uv_sphere(), scenes.random_texture(64, 32, 9, opaque=True)
+rng = np.random.default_rng(11)
+for f in range(2):
+    r.begin_frame(f)
+    r.clear((0.1, 0.6, 0.3))
+    r.mesh(mesh, tex, scenes.SHADE_GOURAUD, (1, -1, 1), (1, 1, 1, 1), (0, 0, 0),
+           scenes.transform7(20.0 + 50 * f, (0, 1, 0), (1, 1, 1)))
+    for _ in range(40):   # rotated (inexact) and plain flat triangles over the mesh, opaque
+        p = np.concatenate([rng.integers(-40, [w + 40, h + 40], (3, 2)), rng.uniform(0, 12, (3, 1))], 1).astype(np.float32)
+        r.triangle(p.reshape(-1), (*rng.random(3).tolist(), 1.0),
+                   scenes.transform7(float(rng.uniform(0, 90)), (0.33, 0.33, 0.33), (1, 1, 1)) if rng.random() < 0.5 else None)
+r.flush()
+d = r.last_pass_deferred()
+out = hashlib.sha256()
+for f in range(2):
+    col, z = r.end_frame(f)
+    out.update(col.tobytes()); out.update(z.tobytes())
+print("RESULT", int(d), out.hexdigest(), r.stats()["setPixels"])
+"""
+
+
+def _run_defer_script(env_value):
+    env = dict(os.environ)
+    env.pop("DTR_B200_DEFER", None)
+    if env_value is not None:
+        env["DTR_B200_DEFER"] = env_value
+    p = subprocess.run([sys.executable, "-c", _DEFER_SCRIPT % {"root": ROOT}], capture_output=True, text=True, env=env, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("RESULT")][-1].split()
+    return int(line[1]), line[2], line[3]
+
+
+def test_deferred_stage_equals_the_single_kernel_stage(built):
+    """A pass made of opaque triangles runs as raster_vis_kernel + resolve_kernel; DTR_B200_DEFER=0
+    forces the single-kernel stage.  Same frames (colour and depth, both frames, odd frame size,
+    exact and inexact triangles) and the same SetPixel count either way."""
+    d1, h1, n1 = _run_defer_script(None)
+    d0, h0, n0 = _run_defer_script("0")
+    assert (d1, d0) == (1, 0), "the deferred stage did not engage / did not switch off"
+    assert h1 == h0, "deferred and single-kernel frames differ"
+    assert n1 == n0, "SetPixel counts differ"
+
+
+def test_deferred_stage_only_for_passes_that_never_blend(built):
+    """One translucent primitive, a texture with a non-opaque texel, or a frame that continues from
+    its previous contents: the pass takes the single-kernel stage.  Every case is checked against the
+    oracle as well."""
+    w, h = 256, 160
+    mesh = scenes.uv_sphere()
+    tr = scenes.transform7(35.0, (0, 1, 0), (1, 1, 1))
+    opaque_tex = scenes.random_texture(32, 32, 4, opaque=True)
+    alpha_tex = scenes.random_texture(32, 32, 4, opaque=False)
+
+    def run(tex, rect_alpha=None, second_pass=False):
+        o, r = _oracle(w, h), _renderer(w, h)
+        r.begin_frame(0)
+        for t in (o, r):
+            t.clear((0.3, 0.3, 0.7))
+            t.mesh(mesh, tex, scenes.SHADE_GOURAUD, (1, -1, 1), (1, 1, 1, 1), (0, 0, 0), tr)
+            if rect_alpha is not None:
+                t.rectangle(mn=(10.0, 20.0), mx=(90.0, 70.0), color=(1.0, 0.5, 0.2, rect_alpha), transform=scenes.DEFAULT_TRANSFORM)
+        r.flush()
+        first = r.last_pass_deferred()
+        second = None
+        if second_pass:  # more opaque triangles onto the frame as it is: no clear, so nothing to defer onto
+            p = np.array([20, 20, 3, 200, 40, 3, 90, 150, 3], np.float32)
+            for t in (o, r):
+                t.triangle(p, (0.9, 0.1, 0.1, 1.0), scenes.DEFAULT_TRIANGLE_TRANSFORM)
+            r.flush()
+            second = r.last_pass_deferred()
+        col, z = r.end_frame(0)
+        _same(col, z, o)
+        return first, second
+
+    assert run(opaque_tex) == (True, None)
+    assert run(alpha_tex)[0] is False
+    assert run(opaque_tex, rect_alpha=0.5)[0] is False
+    assert run(opaque_tex, second_pass=True) == (True, False)
