@@ -40,6 +40,9 @@ constexpr int      VIS_CTAS_PER_SM = 6;
 #ifndef DTR_VIS_SMALL_WINDOWS
 #define DTR_VIS_SMALL_WINDOWS 0 // N > 0: exact triangles whose clipped bbox is at most N 8x4 windows skip the sub-block table (measured: 8 -> +2 %, 16 -> +6 % raster time; the table path culls hidden sub-blocks, this one cannot)
 #endif
+#ifndef DTR_RESOLVE_STREAMS_EMPTY
+#define DTR_RESOLVE_STREAMS_EMPTY 0
+#endif
 #ifndef DTR_VIS_EMPTY_SHIFT
 #define DTR_VIS_EMPTY_SHIFT 0 // (2: no gain) log2 of the untouched tiles per work item of a large launch
 #endif
@@ -550,7 +553,11 @@ __global__ void __launch_bounds__(128, VIS_CTAS_PER_SM) raster_vis_kernel(Raster
 	// last busy regions then start late.)
 	const uint32_t warpsTotal  = gridDim.x * 4u;
 	const uint32_t emptyShift  = nEmpty >= 8u * warpsTotal ? (uint32_t)DTR_VIS_EMPTY_SHIFT : 0u;
+#if DTR_RESOLVE_STREAMS_EMPTY
+	const uint32_t emptyItems  = 0u; // the resolve kernel streams the untouched tiles
+#else
 	const uint32_t emptyItems  = (nEmpty + (1u << emptyShift) - 1u) >> emptyShift;
+#endif
 	const uint32_t itemsBusy   = 2 * nBig + (nSmall << smallShift);
 	const uint32_t itemsMixed  = itemsBusy + (uint32_t)(((unsigned long long)emptyItems * (100 - RASTER_TAIL_PERCENT)) / 100);
 	const uint32_t itemsTotal  = itemsBusy + emptyItems;
@@ -667,8 +674,57 @@ __global__ void __launch_bounds__(256, DTR_RESOLVE_MIN_CTAS) resolve_kernel(Reso
 #else
 	const int      px0 = (int)threadIdx.x & (TILE_W - 1), py0 = (int)threadIdx.x / TILE_W; // pixel of the first of the thread's rows
 #endif
+#if DTR_RESOLVE_STREAMS_EMPTY
+	// Untouched tiles (their clear colour and depth, generated here) are streamed by this kernel, a few
+	// after every busy tile of the CTA: 64 resident warps per SM hide the item latency that the
+	// visibility kernel's 24 cannot, and the HBM write stream overlaps the shading's L2 waits.
+	const uint32_t nEmpty   = R.numTiles - nBusy;
+	const uint32_t perBusy  = nBusy ? (nEmpty + nBusy - 1u) / nBusy : 0u;
+	uint32_t       nextEmpty = blockIdx.x;
+	auto stream_tile = [&](const uint32_t e) {
+		const uint32_t slot = R.numTiles - 1u - e;
+		const uint32_t fr   = __ldg(&R.order[2 * slot].w);
+		const uint4    d1   = __ldg(R.order + 2 * slot + 1);
+		const bool     genZ = (d1.y & FI_Z_RESET) != 0, genC = (d1.y & FI_COLOR_CLEAR) != 0;
+		const int      gx0 = (int)(d1.z & 0xFFFFu) * TILE_W, gy0 = (int)(d1.z >> 16) * TILE_H;
+		uint32_t      *gC = R.color + plane * fr;
+		float         *gZ = R.depth + plane * fr;
+		const float    zInit = -FLT_MAX;
+		if ((R.g.width & 3) == 0)
+		{
+			const int xq = gx0 + ((int)threadIdx.x & 15) * 4;
+#pragma unroll
+			for (int h = 0; h < 2; h++)
+			{
+				const int yq = gy0 + ((int)threadIdx.x >> 4) + 16 * h;
+				if (xq < R.g.width && yq < R.g.height)
+				{
+					const size_t gi = (size_t)yq * R.g.width + xq;
+					if (genC) frame_store(reinterpret_cast<uint4 *>(gC + gi), make_uint4(d1.x, d1.x, d1.x, d1.x));
+					if (genZ) frame_store(reinterpret_cast<float4 *>(gZ + gi), make_float4(zInit, zInit, zInit, zInit));
+				}
+			}
+		}
+		else
+		{
+			for (int i = (int)threadIdx.x; i < TILE_W * TILE_H; i += 256)
+			{
+				const int xq = gx0 + (i & (TILE_W - 1)), yq = gy0 + i / TILE_W;
+				if (xq < R.g.width && yq < R.g.height)
+				{
+					const size_t gi = (size_t)yq * R.g.width + xq;
+					if (genC) gC[gi] = d1.x;
+					if (genZ) gZ[gi] = zInit;
+				}
+			}
+		}
+	};
+#endif
 	for (uint32_t slot = blockIdx.x; slot < nBusy; slot += gridDim.x)
 	{
+#if DTR_RESOLVE_STREAMS_EMPTY
+		for (uint32_t j = 0; j < perBusy && nextEmpty < nEmpty; j++, nextEmpty += gridDim.x) stream_tile(nextEmpty);
+#endif
 		const uint4 d0 = __ldg(R.order + 2 * slot), d1 = __ldg(R.order + 2 * slot + 1);
 		const int   x = (int)(d1.z & 0xFFFFu) * TILE_W + px0, yTop = (int)(d1.z >> 16) * TILE_H + py0;
 		uint32_t   *col = R.color + plane * d0.w + (size_t)yTop * R.g.width + x;
@@ -707,4 +763,7 @@ __global__ void __launch_bounds__(256, DTR_RESOLVE_MIN_CTAS) resolve_kernel(Reso
 			frame_store_u32(col + (size_t)k * (256 / TILE_W) * R.g.width, shade_opaque_from_record(rec, (float)E1, (float)E2, (float)E3));
 		}
 	}
+#if DTR_RESOLVE_STREAMS_EMPTY
+	for (; nextEmpty < nEmpty; nextEmpty += gridDim.x) stream_tile(nextEmpty);
+#endif
 }

@@ -127,6 +127,8 @@ struct ResolveParams
 	const PrimRecord *prims;
 	const uint4      *order;   // tile descriptors in work order: the busy tiles are the first *numBusy
 	const uint32_t   *numBusy;
+	float            *depth;    // [F][H][W] (only written: the clear values of untouched tiles, DTR_RESOLVE_STREAMS_EMPTY)
+	uint32_t          numTiles; // tiles of the pass (busy + untouched)
 	Geometry          g;
 };
 

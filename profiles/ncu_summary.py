@@ -1,7 +1,10 @@
 #!/usr/bin/env python
-"""Turn one `ncu --set full` report into the summaries kept under profiles/:
-   <tag>_raster_details.txt  (ncu --page details), <tag>_raster_raw.json (selected raw metrics),
-   <tag>_raster_lines.txt (per-source-line shares, ncu_lines.py) and the dram traffic per launch.
+"""Turn one `ncu --set full` report into the summaries kept under profiles/.  A report may hold several
+kernels (the deferred raster stage is raster_vis_kernel + resolve_kernel, captured in one ncu pass);
+per kernel <k>:
+   <tag>_<k>_details.txt  (ncu --page details), <tag>_<k>_raw.json (selected raw metrics),
+   <tag>_<k>_lines.txt (per-source-line shares, ncu_lines.py)
+and the dram traffic of the STAGE (sum over the report's kernels) per frame -> raster_traffic.json.
 usage: ncu_summary.py gpurun_out/X.ncu-rep <tag> [workload-key-for-raster_traffic.json views-in-the-captured-launch]"""
 import csv
 import io
@@ -15,23 +18,16 @@ key = sys.argv[3] if len(sys.argv) > 3 else None
 views = int(sys.argv[4]) if len(sys.argv) > 4 else 64
 here = os.path.dirname(os.path.abspath(__file__))
 
-details = subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout
-open(os.path.join(here, f"{tag}_raster_details.txt"), "w").write(details)
-
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(raw)))
-names, units, vals = rows[0], rows[1], rows[2]
-want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__shared_mem_per_block_static", "launch__occupancy_limit_shared_mem",
         "launch__occupancy_limit_registers", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-        "smsp__thread_inst_executed_per_inst_executed.ratio", "launch__grid_size", "launch__block_size"]
-out = {}
-for n, u, v in zip(names, units, vals):
-    if n in want:
-        out[n] = {"value": v, "unit": u}
-json.dump(out, open(os.path.join(here, f"{tag}_raster_raw.json"), "w"), indent=1)
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "launch__grid_size", "launch__block_size",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
 
 
 def to_bytes(m):
@@ -39,20 +35,46 @@ def to_bytes(m):
     return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
 
 
-traffic = to_bytes(out["dram__bytes_read.sum"]) + to_bytes(out["dram__bytes_write.sum"])
-print("dram traffic per launch:", traffic)
+def ncu(*args):
+    return subprocess.run(["ncu", "-i", rep, *args], capture_output=True, text=True).stdout
+
+
+raw = ncu("--page", "raw", "--csv")
+rows = list(csv.reader(io.StringIO(raw)))
+names, units = rows[0], rows[1]
+ik = names.index("Kernel Name")
+kernels = []
+for vals in rows[2:]:
+    if len(vals) <= ik:
+        continue
+    short = vals[ik].split("(")[0].split("::")[-1]
+    if short in [k for k, _ in kernels]:
+        continue  # (one launch per kernel is summarised: the first)
+    kernels.append((short, {n: {"value": v, "unit": u} for n, u, v in zip(names, units, vals) if n in WANT}))
+
+read = write = 0.0
+parts = []
+for short, out in kernels:
+    json.dump(out, open(os.path.join(here, f"{tag}_{short}_raw.json"), "w"), indent=1)
+    open(os.path.join(here, f"{tag}_{short}_details.txt"), "w").write(ncu("--page", "details", "--kernel-name", short))
+    src = ncu("--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", short)
+    tmp = f"/tmp/{tag}_{short}_both.csv"
+    open(tmp, "w").write(src)
+    lines = subprocess.run([sys.executable, os.path.join(here, "ncu_lines.py"), tmp, "60"], capture_output=True, text=True).stdout
+    open(os.path.join(here, f"{tag}_{short}_lines.txt"), "w").write(lines)
+    r, w = to_bytes(out["dram__bytes_read.sum"]), to_bytes(out["dram__bytes_write.sum"])
+    read, write = read + r, write + w
+    parts.append(f"{short}: {out['gpu__time_duration.sum']['value']} {out['gpu__time_duration.sum']['unit']}, "
+                 f"dram read {r / 1e6:.1f} MB + write {w / 1e6:.1f} MB")
+    print(short, out["gpu__time_duration.sum"], "issue active", out["smsp__issue_active.avg.pct_of_peak_sustained_active"]["value"])
+    print(lines[:400])
+
+traffic = read + write
+print("dram traffic of the stage per launch:", traffic)
 if key:
     p = os.path.join(here, "raster_traffic.json")
     t = json.load(open(p)) if os.path.exists(p) else {}
     t[key] = {"bytes_per_frame": int(traffic / views),
-              "source": (f"profiles/{tag}_raster_raw.json (ncu --set full, one raster launch of {views} views: "
-                         f"dram read {to_bytes(out['dram__bytes_read.sum']) / 1e6:.1f} MB + write "
-                         f"{to_bytes(out['dram__bytes_write.sum']) / 1e6:.1f} MB)")}
+              "source": (f"profiles/{tag}_*_raw.json (one ncu --set full pass over the raster stage of {views} views; "
+                         + "; ".join(parts) + ")")}
     json.dump(t, open(p, "w"), indent=1)
-
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
-tmp = f"/tmp/{tag}_both.csv"
-open(tmp, "w").write(src)
-lines = subprocess.run([sys.executable, os.path.join(here, "ncu_lines.py"), tmp, "60"], capture_output=True, text=True).stdout
-open(os.path.join(here, f"{tag}_raster_lines.txt"), "w").write(lines)
-print(lines[:600])

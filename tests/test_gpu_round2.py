@@ -328,3 +328,57 @@ def test_deferred_stage_only_for_passes_that_never_blend(built):
     assert run(alpha_tex)[0] is False
     assert run(opaque_tex, rect_alpha=0.5)[0] is False
     assert run(opaque_tex, second_pass=True) == (True, False)
+
+
+@pytest.mark.parametrize("seed,size", [(1, (257, 131)), (2, (640, 360)), (3, (97, 1000)), (4, (1023, 66)), (5, (1920, 1080))])
+def test_fuzz_opaque_passes_take_the_deferred_stage(built, seed, size):
+    """Random passes made ONLY of opaque triangles -- integer-vertex batches, transformed (inexact)
+    triangles, textured triangles and meshes in all three light modes with an opaque texture -- in one
+    flush at awkward sizes: the deferred stage engages, and colour, depth and the SetPixels counter
+    equal the oracle's (the counter is order dependent: every fragment that passes the depth test when
+    it is submitted counts, whether or not a later one replaces it)."""
+    rng = np.random.default_rng(2000 + seed)
+    w, h = size
+    tex = scenes.random_texture(int(rng.integers(2, 64)), int(rng.integers(2, 64)), 30 + seed, opaque=True)
+    mesh = scenes.uv_sphere(14, 7)
+    o, r = _oracle(w, h), _renderer(w, h)
+    o.reset_counters()
+    r.begin_frame(0)
+    both = (o, r)
+    clear = tuple(rng.random(3))
+    for t in both:
+        t.clear(clear)
+    for i in range(90):
+        kind = int(rng.integers(0, 4))
+        col = (*rng.random(3).tolist(), 1.0)
+        if kind == 0:
+            n = int(rng.integers(1, 60))
+            c = rng.integers(-10, [w + 10, h + 10], (n, 1, 2))
+            p = np.concatenate([c + rng.integers(-40, 41, (n, 3, 2)), rng.uniform(0, 255, (n, 3, 1))], 2).astype(np.float32)
+            cols = rng.random((n, 4)).astype(np.float32)
+            cols[:, 3] = 1.0
+            for t in both:
+                t.triangles(p.reshape(n, 9), cols, scenes.DEFAULT_TRIANGLE_TRANSFORM)
+        elif kind == 1:
+            p = np.concatenate([rng.uniform(-40, [w + 40, h + 40], (3, 2)), rng.uniform(0, 255, (3, 1))], 1).astype(np.float32)
+            tri_tr = scenes.transform7(float(rng.uniform(-3, 3)), tuple(rng.random(3)),
+                                       (float(rng.uniform(0.4, 2.5)), float(rng.uniform(0.4, 2.5)), 1.0))
+            for t in both:
+                t.triangle(p.reshape(-1), col, tri_tr)
+        elif kind == 2:
+            p = np.concatenate([rng.integers(-20, [w + 20, h + 20], (3, 2)), rng.uniform(0, 255, (3, 1))], 1).astype(np.float32)
+            uv = (rng.random(6) * 0.999).astype(np.float32)
+            for t in both:
+                t.textured_triangle(p.reshape(-1), uv, tex, col, scenes.DEFAULT_TRIANGLE_TRANSFORM)
+        elif i % 4 == 0:
+            mode = int(rng.integers(0, 3))
+            view = scenes.view_transforms(4096)[int(rng.integers(0, 4096))]
+            mtex = tex if rng.random() < 0.5 else scenes.WHITE_TEXTURE
+            pos = (float(rng.uniform(-0.3, 0.3)), 0.0, 0.0)
+            for t in both:
+                t.mesh(mesh, mtex, mode, (1, -1, 1), (1, 1, 1, 1), pos, view)
+    r.flush()
+    assert r.last_pass_deferred(), "an all-opaque pass onto cleared frames did not take the deferred stage"
+    col_, z_ = r.end_frame(0)
+    _same(col_, z_, o)
+    assert r.stats()["setPixels"] == o.counters()[0]

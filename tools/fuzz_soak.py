@@ -9,6 +9,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 import test_gpu_parity as t  # noqa: E402
+import test_gpu_round2 as t2  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 rng = np.random.default_rng(77)
@@ -20,5 +21,10 @@ for seed in range(100, 100 + n):
     except AssertionError as e:
         bad.append((seed, size, str(e)[:120]))
         print("FAIL", seed, size, str(e)[:200], flush=True)
-print(f"fuzz soak: {n} seeds, {len(bad)} failures", bad)
+    try:  # the all-opaque variant: these passes take the deferred stage (visibility + resolve kernels)
+        t2.test_fuzz_opaque_passes_take_the_deferred_stage(True, seed, size)
+    except AssertionError as e:
+        bad.append(("opaque", seed, size, str(e)[:120]))
+        print("FAIL opaque", seed, size, str(e)[:200], flush=True)
+print(f"fuzz soak: {n} seeds x 2 kinds, {len(bad)} failures", bad)
 sys.exit(1 if bad else 0)
