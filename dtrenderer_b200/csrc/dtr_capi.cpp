@@ -447,6 +447,7 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	RasterParams R;
 	R.color      = c->outColor;
 	R.depth      = c->outDepth;
+	R.tagColor   = c->dColor;
 	R.frames     = dFrames;
 	R.prims      = (const PrimRecord *)S.prims.p;
 	R.bounds     = (const PrimBounds *)S.bounds.p;
@@ -588,14 +589,16 @@ int do_flush(dtr_b200_ctx *c)
 	c->last.anyTextured = false;
 	for (uint32_t i = 0; i < numItems; i++) c->last.anyTextured = c->last.anyTextured || (it[i].type != ITEM_RAW && it[i].texId >= 0);
 	// Deferred pass (dtr_deferred.cuh): only when nothing can ever be blended -- every primitive an opaque
-	// triangle, every frame starting from an on-chip clear -- and the frames are this context's own planes
-	// (the resolve kernel reads what the visibility kernel wrote; over NVLink that would be a read-back).
+	// triangle, every frame starting from an on-chip clear.  (With foreign output planes -- a band written
+	// into another GPU's frame -- the visibility kernel leaves its tags in this context's own colour planes
+	// and the resolve kernel stores every pixel of the busy tiles to the output: nothing is read back over
+	// NVLink.)
 	{
 		static const bool allow = [] {
 			const char *e = getenv("DTR_B200_DEFER"); // "0": always the single-kernel raster stage
 			return !(e && e[0] == '0');
 		}();
-		bool deferred = allow && numItems > 0 && c->outColor == c->dColor;
+		bool deferred = allow && numItems > 0;
 		for (uint32_t s2 = 0; s2 < numActive && deferred; s2++) deferred = (fs[s2].init & FI_COLOR_CLEAR) != 0;
 		for (uint32_t i = 0; i < numItems && deferred; i++) deferred = c->rec[i].item.type != ITEM_RAW && c->rec[i].opaque;
 		c->last.deferred = deferred;

@@ -47,6 +47,7 @@ constexpr int      VIS_CTAS_PER_SM = 6;
 #define DTR_VIS_EMPTY_SHIFT 0 // (2: no gain) log2 of the untouched tiles per work item of a large launch
 #endif
 constexpr uint32_t VIS_PENDING     = 0x80000000u;
+constexpr uint32_t VIS_OUTSIDE     = 0x40000000u; // resolve_kernel: a pixel of the tile that lies outside the frame (no colour has this bit)
 
 // The reference's per-fragment arithmetic after the depth test for an OPAQUE fragment (SlowTriangle
 // :1177-1222, SetPixel :124-191 with a == 1): barycentrics, Gouraud, nearest texel, modulate, gamma-2
@@ -620,7 +621,8 @@ __global__ void __launch_bounds__(128, VIS_CTAS_PER_SM) raster_vis_kernel(Raster
 		const uint4 d0 = __ldg(P.order + 2 * slot), d1 = __ldg(P.order + 2 * slot + 1);
 		const int   tx = (int)(d1.z & 0xFFFFu), ty = (int)(d1.z >> 16);
 		const bool  genZ = (d1.y & FI_Z_RESET) != 0, genC = (d1.y & FI_COLOR_CLEAR) != 0;
-		uint32_t   *gC = P.color + plane * d0.w;
+		// a tile with primitives goes to the tag planes (the context's own; resolve_kernel finishes it into the output)
+		uint32_t   *gC = (d0.y ? P.tagColor : P.color) + plane * d0.w;
 		float      *gZ = P.depth + plane * d0.w;
 		RegionJob J;
 		J.gx   = tx * TILE_W + rx;
@@ -668,6 +670,7 @@ __global__ void __launch_bounds__(256, DTR_RESOLVE_MIN_CTAS) resolve_kernel(Reso
 	constexpr int  PER_THREAD = TILE_W * TILE_H / 256;
 	const uint32_t nBusy = *R.numBusy;
 	const size_t   plane = (size_t)R.g.width * R.g.height;
+	const bool     split = R.tags != R.color; // foreign output planes: every pixel of a busy tile is stored
 #if DTR_RESOLVE_BLOCKS
 	// a warp takes an 8x4 block of pixels (four 32-byte row segments): fewer distinct triangles per warp
 	const int      px0 = ((int)threadIdx.x >> 5) * 8 + ((int)threadIdx.x & 7), py0 = ((int)threadIdx.x >> 3) & 3;
@@ -727,7 +730,9 @@ __global__ void __launch_bounds__(256, DTR_RESOLVE_MIN_CTAS) resolve_kernel(Reso
 #endif
 		const uint4 d0 = __ldg(R.order + 2 * slot), d1 = __ldg(R.order + 2 * slot + 1);
 		const int   x = (int)(d1.z & 0xFFFFu) * TILE_W + px0, yTop = (int)(d1.z >> 16) * TILE_H + py0;
-		uint32_t   *col = R.color + plane * d0.w + (size_t)yTop * R.g.width + x;
+		const size_t    pix = plane * d0.w + (size_t)yTop * R.g.width + x;
+		uint32_t       *col = R.color + pix;
+		const uint32_t *tag = R.tags + pix;
 		// all of the thread's tags first: eight independent loads in flight (the tags come from DRAM: the
 		// visibility kernel wrote a gigabyte of frames since it stored them)
 		uint32_t v[PER_THREAD];
@@ -735,7 +740,7 @@ __global__ void __launch_bounds__(256, DTR_RESOLVE_MIN_CTAS) resolve_kernel(Reso
 		for (int k = 0; k < PER_THREAD; k++)
 		{
 			const int y = yTop + k * (256 / TILE_W);
-			v[k] = (x < R.g.width && y < R.g.height) ? __ldcs(col + (size_t)k * (256 / TILE_W) * R.g.width) : 0u;
+			v[k] = (x < R.g.width && y < R.g.height) ? __ldcs(tag + (size_t)k * (256 / TILE_W) * R.g.width) : VIS_OUTSIDE;
 		}
 #if DTR_RESOLVE_PREFETCH
 		// the records the thread is going to read, on their way into L1 while the first pixel is shaded
@@ -751,7 +756,12 @@ __global__ void __launch_bounds__(256, DTR_RESOLVE_MIN_CTAS) resolve_kernel(Reso
 		DTR_RESOLVE_UNROLL_PRAGMA(DTR_RESOLVE_UNROLL)
 		for (int k = 0; k < PER_THREAD; k++)
 		{
-			if (!(v[k] & VIS_PENDING)) continue;
+			if (!(v[k] & VIS_PENDING))
+			{
+				// finished already (clear colour, or an inexact triangle's fragment): in place, unless the output is elsewhere
+				if (split && v[k] != VIS_OUTSIDE) frame_store_u32(col + (size_t)k * (256 / TILE_W) * R.g.width, v[k]);
+				continue;
+			}
 			const int    y   = yTop + k * (256 / TILE_W);
 			const uint4 *rec = reinterpret_cast<const uint4 *>(R.prims + (v[k] & ~VIS_PENDING));
 			const uint4  q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);

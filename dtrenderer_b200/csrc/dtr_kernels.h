@@ -74,6 +74,9 @@ struct RasterParams
 {
 	uint32_t           *color; // [F][H][W]
 	float              *depth;
+	uint32_t           *tagColor; // deferred stage: where the visibility kernel leaves the colour tiles of busy tiles (pending
+	                              // tags included) for the resolve kernel -- the context's OWN colour planes; == color unless
+	                              // the output planes are foreign (another GPU's memory)
 	const FrameState   *frames;
 	const PrimRecord   *prims;
 	const PrimBounds   *bounds;
@@ -123,7 +126,10 @@ void launch_flatten_faces(const FlattenParams &P, cudaStream_t s);
 
 struct ResolveParams
 {
-	uint32_t         *color;   // [F][H][W]: finished colours and pending primitive tags
+	uint32_t         *color;   // [F][H][W]: the output colour planes
+	const uint32_t   *tags;    // [F][H][W]: finished colours and pending primitive tags of the busy tiles (== color, or the
+	                           // context's own planes when the output planes are foreign: every pixel of a busy tile is
+	                           // then stored to `color`, pending or not)
 	const PrimRecord *prims;
 	const uint4      *order;   // tile descriptors in work order: the busy tiles are the first *numBusy
 	const uint32_t   *numBusy;

@@ -382,3 +382,53 @@ def test_fuzz_opaque_passes_take_the_deferred_stage(built, seed, size):
     col_, z_ = r.end_frame(0)
     _same(col_, z_, o)
     assert r.stats()["setPixels"] == o.counters()[0]
+
+
+@pytest.mark.parametrize("two_gpus", [False, True])
+def test_deferred_stage_with_foreign_output_planes(built, two_gpus):
+    """A band context whose output planes belong to ANOTHER context (the peer write-back of the band
+    split): the visibility kernel leaves its tags in the band context's own colour planes, the resolve
+    kernel stores every pixel of the busy tiles to the output.  Two bands of an all-opaque scene (odd
+    frame width: the scalar paths), assembled in the first context's planes, equal the oracle's frame."""
+    import torch
+    if two_gpus and torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from dtrenderer_b200 import api
+    w, h = 1021, 600
+    tex = scenes.random_texture(32, 16, 8, opaque=True)
+    rng = np.random.default_rng(21)
+    n = 3000
+    c = rng.integers(0, [w, h], (n, 1, 2))
+    p = np.concatenate([c + rng.integers(-25, 26, (n, 3, 2)), rng.uniform(0, 255, (n, 3, 1))], 2).astype(np.float32)
+    cols = rng.random((n, 4)).astype(np.float32)
+    cols[:, 3] = 1.0
+    rot = scenes.transform7(17.0, (0.33, 0.33, 0.33), (1, 1, 1))
+    big = np.array([40, 30, 2, 980, 200, 2, 500, 590, 2], np.float32)
+
+    def draw(t):
+        t.clear((0.7, 0.2, 0.1))
+        t.mesh(scenes.uv_sphere(), tex, scenes.SHADE_GOURAUD, (1, -1, 1), (1, 1, 1, 1), (0, 0, 0),
+               scenes.transform7(40.0, (0, 1, 0), (1, 1, 1)))
+        t.triangles(p.reshape(n, 9), cols, scenes.DEFAULT_TRIANGLE_TRANSFORM)
+        t.triangle(big, (0.1, 0.9, 0.4, 1.0), rot)  # inexact: shaded inside the visibility kernel
+
+    o = _oracle(w, h)
+    o.reset_counters()
+    draw(o)
+    r0, r1 = api.Renderer(w, h, 1, 0), api.Renderer(w, h, 1, 1 if two_gpus else 0)
+    if two_gpus:
+        r1.enable_peer_access(0)
+    c0, z0 = r0.frame_device_ptrs(0)
+    r1.set_output_planes(c0, z0)
+    y0, y1 = r0.band_rows(2, 0)
+    r0.set_band(y0, y1)
+    r1.set_band(*r1.band_rows(2, 1))
+    for r in (r0, r1):
+        r.begin_frame(0)
+        draw(r)
+        r.flush()
+        assert r.last_pass_deferred()
+    r1.sync()
+    col, z = r0.end_frame(0)
+    _same(col, z, o)
+    assert r0.stats()["setPixels"] + r1.stats()["setPixels"] == o.counters()[0]
