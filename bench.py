@@ -615,9 +615,11 @@ def measure_fill(env, name, n_override, steps, warmup, e2e_steps, gather, with_e
     upload_bytes = st["uploadBytes"]
     alg_bytes = 8 * w * (y1 - y0) + 156 * n  # this rank's band + all triangles (every rank runs setup)
 
+    skip_barrier = os.environ.get("DTR_BENCH_DIAG_NO_BARRIER") == "1"  # diagnostic only: what the barrier costs
+
     def step_resident():
         r.replay()
-        if peer:
+        if peer and not skip_barrier:
             r.band_barrier()  # stream-ordered: every band has landed in rank 0's HBM
         elif nccl:
             r.gather_bands(0, dst=0)
