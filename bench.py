@@ -66,6 +66,14 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def kernel_split(split, runs, deferred, textured):
+    """CUDA-event durations of the raster stage's kernels inside the timed region (dtr_b200_get_raster_split_ms)."""
+    a, b = split[0] / max(runs, 1), split[1] / max(runs, 1)
+    if deferred:
+        return {"raster_vis_kernel": a, "resolve_kernel": b}
+    return {"raster_tex_kernel" if textured else "raster_kernel": a}
+
+
 def load_traffic(workload):
     """(dram bytes per frame, source) from the committed ncu capture of this workload's raster kernel, or
     (None, None).  A constant read from profiles/, NOT a measurement of the run that prints it."""
@@ -394,6 +402,7 @@ def measure_views(env, name, views, steps, warmup, e2e_steps, with_e2e):
     env.clocks.pause()
     ms_step = env.max_over_ranks(e0.elapsed_time(e1)) / steps
     stage, runs = r.stage_ms()
+    split, _ = r.raster_split_ms()
     env.launches += r.stats()["kernelLaunches"]
     deferred = r.last_pass_deferred()
     # parity of what the TIMED path left in the frames: first, middle and last view of this rank
@@ -430,6 +439,7 @@ def measure_views(env, name, views, steps, warmup, e2e_steps, with_e2e):
                      "traffic_source": (tr_src + " (a committed capture scaled to this batch, not measured in this run)") if tr_src else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": raster_ms,
                      "stage_ms_per_step": {k: v / max(runs, 1) for k, v in stage.items()},
+                     "raster_kernels_ms_per_step": kernel_split(split, runs, deferred, s["textured"]),
                      "stage_ms_isolated": {k: v / max(runs_iso, 1) for k, v in stage_iso.items()},
                      "note": "achieved/frac use the raster kernel's CUDA-event duration inside the timed region, where "
                              "setup/scan/bin of later replays run on a second stream beside it (their stage_ms_per_step "
@@ -640,6 +650,7 @@ def measure_fill(env, name, n_override, steps, warmup, e2e_steps, gather, with_e
     env.clocks.pause()
     ms_step = env.max_over_ranks(e0.elapsed_time(e1)) / steps
     stage, runs = r.stage_ms()
+    split, _ = r.raster_split_ms()
     env.launches += r.stats()["kernelLaunches"]
     deferred = r.last_pass_deferred()
     r.set_profiling(False)
@@ -688,6 +699,7 @@ def measure_fill(env, name, n_override, steps, warmup, e2e_steps, gather, with_e
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": raster_ms,
                      "stage_ms_per_step": {k: v / max(runs, 1) for k, v in stage.items()},
+                     "raster_kernels_ms_per_step": kernel_split(split, runs, deferred, False),
                      "note": "rank 0's band; this config is ALU/ordering bound, not HBM bound; the frame planes (66 MB) fit "
                              "in L2, the 160 MB of primitive records do not, L2 is not flushed between steps"},
     }

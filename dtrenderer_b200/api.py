@@ -98,6 +98,7 @@ SYMBOLS = [
     ("dtr_b200_last_pass_deferred", C.c_int, [C.c_void_p]),
     ("dtr_b200_set_profiling", C.c_int, [C.c_void_p, C.c_int]),
     ("dtr_b200_get_stage_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float * 4), C.POINTER(C.c_int)]),
+    ("dtr_b200_get_raster_split_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float * 2), C.POINTER(C.c_int)]),
     ("dtr_b200_reset_stage_ms", C.c_int, [C.c_void_p]),
     ("dtr_b200_selftest", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     ("dtr_b200_clear", C.c_int, [C.c_void_p, _f]),
@@ -418,6 +419,13 @@ class Renderer:
         ms, runs = (C.c_float * 4)(), C.c_int(0)
         self._ck(self.lib.dtr_b200_get_stage_ms(self.ctx, C.byref(ms), C.byref(runs)))
         return dict(setup=ms[0], scan=ms[1], bin=ms[2], raster=ms[3]), runs.value
+
+    def raster_split_ms(self):
+        """Summed device ms of the raster stage's kernels: (first kernel = visibility or the single raster
+        kernel, resolve kernel), and the number of pipelines timed."""
+        ms, runs = (C.c_float * 2)(), C.c_int(0)
+        self._ck(self.lib.dtr_b200_get_raster_split_ms(self.ctx, C.byref(ms), C.byref(runs)))
+        return (ms[0], ms[1]), runs.value
 
     def selftest(self):
         """Mismatches of the device arithmetic self-test (must be 0)."""

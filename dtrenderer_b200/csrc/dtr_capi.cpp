@@ -293,7 +293,7 @@ int record_tris(dtr_b200_ctx *c, int n, const float *p, const float *color, cons
 	return 0;
 }
 
-constexpr int EVENTS_PER_RUN = 6; // pre start, after setup, after scan, after bin | raster start, raster end
+constexpr int EVENTS_PER_RUN = 7; // pre start, after setup, after scan, after bin | raster start, after the stage's first kernel, raster end
 
 int mark(dtr_b200_ctx *c, cudaStream_t stream)
 {
@@ -471,13 +471,15 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	if ((rc = mark(c, c->stream))) return rc;
 	if (c->last.deferred)
 	{
-		launch_raster_deferred(R, c->limits, c->stream);
+		// (profiling: the event between the visibility and the resolve kernel)
+		launch_raster_deferred(R, c->limits, c->stream, [](void *ctx, cudaStream_t s2) { mark(static_cast<dtr_b200_ctx *>(ctx), s2); }, c);
 		c->launches += 2;
 	}
 	else
 	{
 		launch_raster(R, c->limits, c->stream);
 		c->launches++;
+		if ((rc = mark(c, c->stream))) return rc; // (a single kernel: the stage's first kernel is all of it)
 	}
 	if ((rc = mark(c, c->stream))) return rc;
 	CU(cudaEventRecord(S.rasterDone, c->stream));
@@ -1409,8 +1411,27 @@ int dtr_b200_get_stage_ms(dtr_b200_ctx *c, float ms[4], int *runs)
 			ms[s2] += t;
 		}
 		float t = 0.0f;
-		CU(cudaEventElapsedTime(&t, ev[4], ev[5]));
+		CU(cudaEventElapsedTime(&t, ev[4], ev[6]));
 		ms[3] += t;
+	}
+	return DTR_B200_OK;
+}
+
+int dtr_b200_get_raster_split_ms(dtr_b200_ctx *c, float ms[2], int *runs)
+{
+	if (!c || !ms || !runs) return DTR_B200_ERR_ARG;
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	ms[0] = ms[1] = 0.0f;
+	*runs = (int)(c->events.size() / EVENTS_PER_RUN);
+	for (int r = 0; r < *runs; r++)
+	{
+		const cudaEvent_t *ev = &c->events[(size_t)EVENTS_PER_RUN * r];
+		float a = 0.0f, b = 0.0f;
+		CU(cudaEventElapsedTime(&a, ev[4], ev[5]));
+		CU(cudaEventElapsedTime(&b, ev[5], ev[6]));
+		ms[0] += a;
+		ms[1] += b;
 	}
 	return DTR_B200_OK;
 }

@@ -147,7 +147,9 @@ void launch_selftest_sqrt(unsigned long long *mismatches, cudaStream_t s);
 void launch_bin(const BinParams &P, const LaunchLimits &L, cudaStream_t s);
 void launch_raster(const RasterParams &P, const LaunchLimits &L, cudaStream_t s);
 // the deferred variant of the raster stage (dtr_deferred.cuh): raster_vis_kernel + resolve_kernel
-void launch_raster_deferred(const RasterParams &P, const LaunchLimits &L, cudaStream_t s);
+// `between` (may be null) is called after the visibility kernel has been launched: the profiling event
+void launch_raster_deferred(const RasterParams &P, const LaunchLimits &L, cudaStream_t s, void (*between)(void *, cudaStream_t) = nullptr,
+                            void *betweenArg = nullptr);
 void launch_premultiply(uint32_t *pixels, size_t count, cudaStream_t s);
 void launch_pack_bgr24(const uint32_t *color, uint32_t *out, int width, size_t rows, int pitchWords, cudaStream_t s);
 

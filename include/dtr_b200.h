@@ -259,10 +259,14 @@ int dtr_b200_last_pass_deferred(const dtr_b200_ctx *ctx);
 int dtr_b200_reset_stats(dtr_b200_ctx *ctx);
 /* Per-stage device timing with CUDA events on the context's stream (the ncu/nsys replacement of
  * the reference's rdtsc region counters, DTRendererDebug.h:42-78).  While enabled, every
- * flush/replay records 6 events; dtr_b200_get_stage_ms syncs and returns the SUMS in ms of
+ * flush/replay records 7 events; dtr_b200_get_stage_ms syncs and returns the SUMS in ms of
  * {setup, scan, bin, raster} over the pipelines run since the last reset, and their number. */
 int dtr_b200_set_profiling(dtr_b200_ctx *ctx, int enable);
 int dtr_b200_get_stage_ms(dtr_b200_ctx *ctx, float ms[4], int *runs);
+/* The raster stage of the same runs, split at the event between its kernels: ms[0] = the stage's first
+ * kernel (the visibility kernel of a deferred pass, or the single raster kernel), ms[1] = the resolve
+ * kernel (0 for a pass that was not deferred).  ms[0] + ms[1] = the raster entry of get_stage_ms. */
+int dtr_b200_get_raster_split_ms(dtr_b200_ctx *ctx, float ms[2], int *runs);
 int dtr_b200_reset_stage_ms(dtr_b200_ctx *ctx);
 
 /* Device self-test of the arithmetic shortcuts: the blend's branch-free square root is compared
