@@ -432,3 +432,33 @@ def test_deferred_stage_with_foreign_output_planes(built, two_gpus):
     col, z = r0.end_frame(0)
     _same(col, z, o)
     assert r0.stats()["setPixels"] + r1.stats()["setPixels"] == o.counters()[0]
+
+
+def test_raster_stage_split_timing(built):
+    """dtr_b200_get_raster_split_ms: with profiling on, a deferred pass reports both of its kernels and
+    their sum is the raster entry of dtr_b200_get_stage_ms; a blended pass reports a single kernel."""
+    w, h = 640, 360
+    mesh, tex = scenes.uv_sphere(), scenes.random_texture(32, 32, 4, opaque=True)
+    tr = scenes.transform7(35.0, (0, 1, 0), (1, 1, 1))
+    for blended in (False, True):
+        r = _renderer(w, h)
+        r.set_profiling(True)
+        r.begin_frame(0)
+        r.clear((0.3, 0.3, 0.7))
+        r.mesh(mesh, tex, scenes.SHADE_GOURAUD, (1, -1, 1), (1, 1, 1, 1), (0, 0, 0), tr)
+        if blended:
+            r.rectangle(mn=(10.0, 20.0), mx=(90.0, 70.0), color=(1.0, 0.5, 0.2, 0.5), transform=scenes.DEFAULT_TRANSFORM)
+        r.flush()
+        for _ in range(3):
+            r.replay()
+        stage, runs = r.stage_ms()
+        (first, second), runs2 = r.raster_split_ms()
+        assert runs == runs2 == 4
+        assert r.last_pass_deferred() == (not blended)
+        assert first > 0.0
+        if blended:
+            assert second < 0.02 * runs  # an empty interval between two events: a few microseconds per run
+        else:
+            assert second > 0.0
+        assert abs((first + second) - stage["raster"]) <= 0.05 * stage["raster"] + 0.01
+        r.close()
