@@ -590,7 +590,7 @@ def run_fill_reference(args, rank, world):
         flush=True)
 
 
-def measure_fill(env, name, n_override, steps, warmup, e2e_steps, gather, with_e2e):
+def measure_fill(env, name, n_override, steps, warmup, e2e_steps, gather, with_e2e, band_frames=2):
     """cfg 4 on this process group: one frame of 1M small triangles; N>1 splits the screen into
     tile-aligned bands (every rank runs setup over all triangles, bins and rasterises its band) and
     assembles the frame in rank 0's HBM.  Parity: the assembled planes == rank 0's own whole-frame
@@ -655,10 +655,59 @@ def measure_fill(env, name, n_override, steps, warmup, e2e_steps, gather, with_e
     deferred = r.last_pass_deferred()
     r.set_profiling(False)
 
-    # ---- parity of the frame the timed steps left in rank 0's HBM ---------------------------
+    # ---- two frame targets per rank (double buffering): frame i's barrier beside frame i+1's rasterisation ----
+    # A second context with its own stream, its own NCCL communicator and its own mapping of rank 0's second
+    # target; consecutive frames alternate between the two.  A frame is complete in rank 0's HBM when ITS
+    # barrier has passed, exactly as before; what changes is that no rank waits for that before it starts
+    # the next frame, which goes to the other target.  The timed interval ends when both streams are done.
+    inline_ms = None
+    r2 = None
+    if peer and band_frames == 2 and not skip_barrier:
+        inline_ms = ms_step
+        r2 = env.api.Renderer(w, h, 1, env.local_rank)
+        s2 = torch.cuda.Stream()
+        r2.set_stream(s2.cuda_stream)
+        r2.set_band(y0, max(y1, y0 + 1) if y1 > y0 else h)
+        r2.band_comm_init_torch(env.dist)
+        multigpu.share_frames(r2, dst=0)
+        r2.begin_frame(0)
+        r2.clear((0, 0, 0))
+        r2.triangles(p, color, scenes.DEFAULT_TRIANGLE_TRANSFORM)
+        with torch.cuda.stream(s2):
+            r2.flush()
+        pair = (r, r2)
+
+        def run_alternating(k):
+            for i in range(k):
+                x = pair[i & 1]
+                x.replay()
+                x.band_barrier()
+
+        run_alternating(2 * max(warmup, 3))
+        env.stream.synchronize()
+        s2.synchronize()
+        env.barrier()
+        steps2 = steps + (steps & 1)
+        env.clocks.start()
+        e0.record(env.stream)
+        s2.wait_stream(env.stream)
+        run_alternating(steps2)
+        env.stream.wait_stream(s2)
+        e1.record(env.stream)
+        env.barrier()
+        env.clocks.pause()
+        ms_step = env.max_over_ranks(e0.elapsed_time(e1)) / steps2
+        env.launches += r2.stats()["kernelLaunches"]
+
+    # ---- parity of the frame(s) the timed steps left in rank 0's HBM ---------------------------
     parity = []
     if rank == 0:
         col, z = r.end_frame(0)
+        if r2 is not None:
+            col_b, z_b = r2.end_frame(0)
+            if not (np.array_equal(col, col_b) and np.array_equal(z.view(np.uint32), z_b.view(np.uint32))):
+                raise SystemExit(f"bench.py: PARITY FAILURE {name}: the two frame targets of the double-buffered band loop differ")
+            parity.append("both frame targets of the double-buffered loop bit-equal to each other")
         if world > 1:
             whole = env.api.Renderer(w, h, 1, env.local_rank)
             whole.begin_frame(0)
@@ -690,8 +739,12 @@ def measure_fill(env, name, n_override, steps, warmup, e2e_steps, gather, with_e
         "mtris_per_s": n / (ms_step * 1e-3) / 1e6, "frames_per_s": 1.0 / (ms_step * 1e-3),
         "parallelism": (f"sort-first bands x{world}, " + (
             "bands written into rank 0's HBM over NVLink by the raster kernel's write-back (CUDA IPC peer memory), "
-            "stream-ordered NCCL barrier (dtr_b200_band_barrier)" if peer
+            "stream-ordered NCCL barrier (dtr_b200_band_barrier)" + (
+                "; two frame targets per rank used alternately: the barrier that completes frame i runs beside the "
+                "rasterisation of frame i+1 (ms_per_step_one_target = the same loop with one target and the barrier in line)"
+                if r2 is not None else "") if peer
             else "grouped ncclSend/ncclRecv gather (dtr_b200_gather_bands)")) if world > 1 else "single GPU, whole frame",
+        "band_frames": 2 if r2 is not None else 1, "ms_per_step_one_target": inline_ms,
         "exchange_bytes_per_step_into_rank0": 8 * w * (h - multigpu.band_rows(h, world, 0, r.tile_height())[1]) if world > 1 else 0,
         "parity_checked": True, "parity": "; ".join(parity),
         "roofline": {"bound": "hbm", "kernel": "raster_vis_kernel + resolve_kernel" if deferred else "raster_kernel",
@@ -728,6 +781,8 @@ def measure_fill(env, name, n_override, steps, warmup, e2e_steps, gather, with_e
         e2e_ms = env.max_over_ranks(e0.elapsed_time(e1)) / e2e_steps
         out["e2e"] = {"value": shaded_per_step / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": upload_bytes,
                       "d2h_bytes_per_step": 4 * w * h, "ms_per_step": e2e_ms, "steps": e2e_steps}
+    if r2 is not None:
+        r2.close()
     r.close()
     return out
 
@@ -743,7 +798,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         bind_to_gpu_numa_node(local_rank)
     e2e_steps = max(2, min(args.steps, args.e2e_steps))
     if main_is_fill:
-        main = measure_fill(env, args.workload, args.triangles, args.steps, args.warmup, e2e_steps, args.gather, True)
+        main = measure_fill(env, args.workload, args.triangles, args.steps, args.warmup, e2e_steps, args.gather, True, args.band_frames)
     else:
         main = measure_views(env, args.workload, views, args.steps, args.warmup, e2e_steps, True)
     others = []
@@ -753,7 +808,7 @@ def run_gpu_arm(args, rank, world, local_rank):
             if name != args.workload:
                 others.append(measure_views(env, name, min(WORKLOADS[name]["views"], 64), o_steps, args.warmup, 0, False))
         if not main_is_fill:
-            others.append(measure_fill(env, "fill4k", args.triangles, o_steps, args.warmup, 0, args.gather, False))
+            others.append(measure_fill(env, "fill4k", args.triangles, o_steps, args.warmup, 0, args.gather, False, args.band_frames))
     clocks = env.clocks.result()
     if rank == 0:
         line = {
@@ -769,6 +824,8 @@ def run_gpu_arm(args, rank, world, local_rank):
             "other_workloads": [{k: v for k, v in o.items() if k not in ("unit",)} for o in others],
             "gpu_launches": env.launches, "clocks": clocks,
         }
+        if main.get("band_frames"):
+            line["band_frames"], line["ms_per_step_one_target"] = main["band_frames"], main["ms_per_step_one_target"]
         if "e2e_bgr24" in main:
             line["e2e_bgr24"] = main["e2e_bgr24"]
         print(json.dumps(line), flush=True)
@@ -808,6 +865,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="measure only the main workload")
+    ap.add_argument("--band-frames", type=int, default=2, choices=[1, 2],
+                    help="fill4k, N>1, peer write-back: frame targets per rank. 2 = consecutive frames alternate between two "
+                         "targets, so the barrier that completes frame i runs beside the rasterisation of frame i+1; "
+                         "1 = one target, the barrier in line (always measured and reported as well)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="fill4k, N>1: how the bands reach rank 0 (peer-memory write-back or NCCL send/recv)")
     args = ap.parse_args()
