@@ -149,29 +149,40 @@ sys.path.insert(0, {root!r})
 from dtrenderer_b200 import api, scenes
 rank, world, mode = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
 w, h = 1024, 768
-r = api.Renderer(w, h, 1, rank)
-if rank == 0:
-    uid = r.band_comm_unique_id()
-    open(sys.argv[4] + ".tmp", "wb").write(uid)
-    os.rename(sys.argv[4] + ".tmp", sys.argv[4])
-else:
-    while not os.path.exists(sys.argv[4]): time.sleep(0.01)
-    uid = open(sys.argv[4], "rb").read()
-r.band_comm_init(uid, world, rank)
-y0, y1 = r.band_rows(world, rank)
-r.set_band(y0, y1)
 scene = scenes.fill_scene(w, h, 20000, seed=11) + scenes.cfg1_scene(w, h)[1:]
-if mode == "peer":
-    # rank 0 exports its planes; the handles travel through a file like the unique id did
+
+def publish(path, data):
+    open(path + ".tmp", "wb").write(data)
+    os.rename(path + ".tmp", path)
+
+def fetch(path):
+    while not os.path.exists(path): time.sleep(0.01)
+    return open(path, "rb").read()
+
+def make(tag):
+    # one band context: its own NCCL communicator and (peer modes) its own mapping of rank 0's planes;
+    # the unique id and the IPC handles travel through files
+    r = api.Renderer(w, h, 1, rank)
+    base = sys.argv[4] + tag
     if rank == 0:
-        hc, hz = r.export_frames()
-        open(sys.argv[4] + ".ipc.tmp", "wb").write(hc + hz); os.rename(sys.argv[4] + ".ipc.tmp", sys.argv[4] + ".ipc")
-    else:
-        while not os.path.exists(sys.argv[4] + ".ipc"): time.sleep(0.01)
-        raw = open(sys.argv[4] + ".ipc", "rb").read()
-        r.open_peer_frames(raw[:64], raw[64:])
-    r.band_barrier()  # rank 0's planes exist and are mapped before anybody writes
-for rep in range(3):
+        publish(base, r.band_comm_unique_id())
+    r.band_comm_init(fetch(base), world, rank)
+    r.set_band(*r.band_rows(world, rank))
+    if mode != "nccl":
+        if rank == 0:
+            hc, hz = r.export_frames()
+            publish(base + ".ipc", hc + hz)
+        else:
+            raw = fetch(base + ".ipc")
+            r.open_peer_frames(raw[:64], raw[64:])
+        r.band_barrier()  # rank 0's planes exist and are mapped before anybody writes
+    return r
+
+# "peer2": two frame targets per rank used alternately (what bench.py's band loop does): the barrier that
+# completes frame i runs beside the rasterisation of frame i+1, each context on its own stream
+ctxs = [make("a"), make("b")] if mode == "peer2" else [make("a")]
+for rep in range(4):
+    r = ctxs[rep % len(ctxs)]
     r.begin_frame(0)
     scenes.replay(scene, r)
     if mode == "nccl":
@@ -179,24 +190,28 @@ for rep in range(3):
     else:
         r.band_barrier()
 if rank == 0:
-    col, z = r.end_frame(0)
     whole = api.Renderer(w, h, 1, 0)
     whole.begin_frame(0)
     scenes.replay(scene, whole)
     c1, z1 = whole.end_frame(0)
-    ok = np.array_equal(col, c1) and np.array_equal(z.view(np.uint32), z1.view(np.uint32))
+    ok = True
+    for r in ctxs:
+        col, z = r.end_frame(0)
+        ok = ok and np.array_equal(col, c1) and np.array_equal(z.view(np.uint32), z1.view(np.uint32))
     print("ASSEMBLED_OK" if ok else "ASSEMBLED_DIFFERS", flush=True)
-r.band_barrier()  # nobody tears its context down while another rank still uses it
-r.sync()
+for r in ctxs:
+    r.band_barrier()  # nobody tears its context down while another rank still uses it
+    r.sync()
 """
 
 
-@pytest.mark.parametrize("mode", ["nccl", "peer"])
+@pytest.mark.parametrize("mode", ["nccl", "peer", "peer2"])
 def test_band_exchange_through_the_c_abi_two_processes(built, tmp_path, mode):
     """Sort-first bands with NO Python on the data path: one process per GPU, the library's own NCCL
     communicator (dtr_b200_band_comm_init), dtr_b200_gather_bands (grouped ncclSend/ncclRecv) or the
-    peer-memory write-back ended by dtr_b200_band_barrier; rank 0's assembled frame must equal its own
-    whole-frame render bit for bit."""
+    peer-memory write-back ended by dtr_b200_band_barrier -- with one frame target per rank or with two
+    used alternately ("peer2": double buffering, each context on its own stream with its own
+    communicator); rank 0's assembled frame(s) must equal its own whole-frame render bit for bit."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
