@@ -253,6 +253,7 @@ __device__ __forceinline__ void process_region_vis(const RasterParams &P, VisSme
 		}
 	};
 
+#if DTR_VIS_SMALL_WINDOWS
 	// exact triangle with a small bounding box: 8x4 WINDOWS laid from the bbox corner instead of the
 	// region's sub-block grid.  A 30-pixel mesh triangle (bbox ~8x8) is two windows but straddles five or
 	// six sub-blocks; and nothing is tabulated first (no classification, no table, no warp barriers).
@@ -305,6 +306,7 @@ __device__ __forceinline__ void process_region_vis(const RasterParams &P, VisSme
 			py += SUB_H;
 		}
 	};
+#endif
 
 	// inexact triangle: the row-shared replay of raster_tri_replay; fragments are shaded at once
 	auto raster_tri_replay = [&](const uint32_t pidx, const uint4 g0, const uint4 g1, const uint4 g2, const uint4 g4) {
