@@ -33,3 +33,25 @@ def test_other_ranks_of_the_reference_arm_exit_quietly(built):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_raster_stage_split_labels():
+    """roofline.raster_kernels_ms_per_step names the kernels the stage really ran: the deferred pair, or the
+    one raster kernel of a pass with blended primitives."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.kernel_split((4.0, 2.0), 2, True, True) == {"raster_vis_kernel": 2.0, "resolve_kernel": 1.0}
+    assert bench.kernel_split((4.0, 0.0), 2, False, True) == {"raster_tex_kernel": 2.0}
+    assert bench.kernel_split((4.0, 0.0), 0, False, False) == {"raster_kernel": 4.0}
+
+
+def test_gpu_arm_fails_loudly_without_a_device(built):
+    """No CPU fallback: on a box without a GPU the B200 arm must not print a line."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a CUDA device is present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0", "--no-cpu-baseline",
+                          "--no-others"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode != 0
+    assert not [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
