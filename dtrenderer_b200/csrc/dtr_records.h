@@ -27,19 +27,9 @@ constexpr int REGION_H    = TILE_H;
 constexpr int SUB_W       = 8;
 constexpr int SUB_H       = 4;
 // Warp pairs (see dtr_kernels.cu): a raster CTA is four producer warps + four consumer warps, four CTAs per SM
-#ifndef DTR_WARP_PAIRS
-#define DTR_WARP_PAIRS 0
-#endif
-#if DTR_WARP_PAIRS
-constexpr int RASTER_THREADS = 256;
-#ifndef DTR_RASTER_CTAS
-#define DTR_RASTER_CTAS 4
-#endif
-#else
 constexpr int RASTER_THREADS = 128;
 #ifndef DTR_RASTER_CTAS
 #define DTR_RASTER_CTAS 5
-#endif
 #endif
 #ifndef DTR_RASTER_TAIL
 #define DTR_RASTER_TAIL 10
