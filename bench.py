@@ -66,21 +66,38 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def kernel_split(split, runs, deferred, textured):
-    """CUDA-event durations of the raster stage's kernels inside the timed region (dtr_b200_get_raster_split_ms)."""
+ONE_KERNEL = "raster_opaque_kernel<true>"                       # dtr_b200_last_pass_deferred() == 2 (the default for opaque-only passes)
+TWO_KERNELS = ("raster_opaque_kernel<false>", "resolve_kernel")  # == 1 (DTR_B200_FUSED=0)
+
+
+def kernel_split(split, runs, stage, textured):
+    """CUDA-event durations of the raster stage's kernels inside the timed region (dtr_b200_get_raster_split_ms).
+    stage: 0 = the single raster kernel, 1 = visibility kernel + resolve kernel, 2 = the one-kernel opaque stage."""
     a, b = split[0] / max(runs, 1), split[1] / max(runs, 1)
-    if deferred:
-        return {"raster_vis_kernel": a, "resolve_kernel": b}
+    if stage == 2:
+        return {ONE_KERNEL: a}
+    if stage == 1:
+        return {TWO_KERNELS[0]: a, TWO_KERNELS[1]: b}
     return {"raster_tex_kernel" if textured else "raster_kernel": a}
 
 
-def load_traffic(workload):
-    """(dram bytes per frame, source) from the committed ncu capture of this workload's raster kernel, or
-    (None, None).  A constant read from profiles/, NOT a measurement of the run that prints it."""
+def stage_label(stage, textured):
+    if stage == 2:
+        return (ONE_KERNEL + " (opaque-only pass: region walk with depth test and primitive tags, then every visible pixel of the "
+                "finished region shaded once from shared memory; one kernel)")
+    if stage == 1:
+        return (" + ".join(TWO_KERNELS) + " (opaque-only pass as two kernels: visibility, then resolve; both inside the timed interval)")
+    return "raster_tex_kernel" if textured else "raster_kernel"
+
+
+def load_traffic(workload, stage=0):
+    """(dram bytes per frame, source) from the committed ncu capture of this workload's raster kernel(s), or
+    (None, None).  A constant read from profiles/, NOT a measurement of the run that prints it.  Entries are
+    keyed by workload; the capture of the one-kernel opaque stage by workload + "@one_kernel"."""
     p = os.path.join(ROOT, "profiles", "raster_traffic.json")
     if os.path.exists(p):
         try:
-            e = json.load(open(p)).get(workload)
+            e = json.load(open(p)).get(workload + "@one_kernel" if stage == 2 else workload)
             if isinstance(e, dict):
                 return e.get("bytes_per_frame"), e.get("source")
         except Exception:
@@ -404,7 +421,7 @@ def measure_views(env, name, views, steps, warmup, e2e_steps, with_e2e):
     stage, runs = r.stage_ms()
     split, _ = r.raster_split_ms()
     env.launches += r.stats()["kernelLaunches"]
-    deferred = r.last_pass_deferred()
+    opaque_stage = r.last_pass_stage()
     # parity of what the TIMED path left in the frames: first, middle and last view of this rank
     pairs = sorted({(0, view0), (B // 2, view0 + B // 2), (B - 1, view0 + B - 1)})
     checked = check_view_frames(r, scene, pairs)
@@ -422,7 +439,7 @@ def measure_views(env, name, views, steps, warmup, e2e_steps, with_e2e):
     peak, peak_src = load_peaks()
     raster_ms = stage["raster"] / max(runs, 1)
     achieved = alg_bytes / (raster_ms * 1e-3) / 1e9 if raster_ms > 0 else 0.0
-    tr_frame, tr_src = load_traffic(name)
+    tr_frame, tr_src = load_traffic(name, opaque_stage)
     world = env.world
     out = {
         "workload": name, "value": world * shaded_per_step / (ms_step * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_step,
@@ -431,15 +448,13 @@ def measure_views(env, name, views, steps, warmup, e2e_steps, with_e2e):
         "parity_checked": True,
         "parity": f"{checked} frames per rank of the timed replay (first, middle, last view) bit-equal in colour and depth "
                   f"to the {oracle_kind()} oracle at {w}x{h}",
-        "roofline": {"bound": "hbm", "kernel": ("raster_vis_kernel + resolve_kernel (deferred raster stage: every primitive an opaque "
-                                                "triangle; both kernels inside the timed interval)") if deferred
-                     else ("raster_tex_kernel" if s["textured"] else "raster_kernel"),
+        "roofline": {"bound": "hbm", "kernel": stage_label(opaque_stage, s["textured"]),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": tr_frame * B if tr_frame else None,
                      "traffic_source": (tr_src + " (a committed capture scaled to this batch, not measured in this run)") if tr_src else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": raster_ms,
                      "stage_ms_per_step": {k: v / max(runs, 1) for k, v in stage.items()},
-                     "raster_kernels_ms_per_step": kernel_split(split, runs, deferred, s["textured"]),
+                     "raster_kernels_ms_per_step": kernel_split(split, runs, opaque_stage, s["textured"]),
                      "stage_ms_isolated": {k: v / max(runs_iso, 1) for k, v in stage_iso.items()},
                      "note": "achieved/frac use the raster kernel's CUDA-event duration inside the timed region, where "
                              "setup/scan/bin of later replays run on a second stream beside it (their stage_ms_per_step "
@@ -652,7 +667,7 @@ def measure_fill(env, name, n_override, steps, warmup, e2e_steps, gather, with_e
     stage, runs = r.stage_ms()
     split, _ = r.raster_split_ms()
     env.launches += r.stats()["kernelLaunches"]
-    deferred = r.last_pass_deferred()
+    opaque_stage = r.last_pass_stage()
     r.set_profiling(False)
 
     # ---- two frame targets per rank (double buffering): frame i's barrier beside frame i+1's rasterisation ----
@@ -747,12 +762,12 @@ def measure_fill(env, name, n_override, steps, warmup, e2e_steps, gather, with_e
         "band_frames": 2 if r2 is not None else 1, "ms_per_step_one_target": inline_ms,
         "exchange_bytes_per_step_into_rank0": 8 * w * (h - multigpu.band_rows(h, world, 0, r.tile_height())[1]) if world > 1 else 0,
         "parity_checked": True, "parity": "; ".join(parity),
-        "roofline": {"bound": "hbm", "kernel": "raster_vis_kernel + resolve_kernel" if deferred else "raster_kernel",
+        "roofline": {"bound": "hbm", "kernel": stage_label(opaque_stage, False),
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": raster_ms,
                      "stage_ms_per_step": {k: v / max(runs, 1) for k, v in stage.items()},
-                     "raster_kernels_ms_per_step": kernel_split(split, runs, deferred, False),
+                     "raster_kernels_ms_per_step": kernel_split(split, runs, opaque_stage, False),
                      "note": "rank 0's band; this config is ALU/ordering bound, not HBM bound; the frame planes (66 MB) fit "
                              "in L2, the 160 MB of primitive records do not, L2 is not flushed between steps"},
     }

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DTR_B200_LIB") or os.path.join(_HERE, "libdtr_b200.so")
 
 SHADE_FULLBRIGHT, SHADE_FLAT, SHADE_GOURAUD = 0, 1, 2
+OPAQUE_SINGLE_KERNEL, OPAQUE_TWO_KERNELS, OPAQUE_ONE_KERNEL = 0, 1, 2  # dtr_b200_set_opaque_stage
 
 _f = C.POINTER(C.c_float)
 _u8 = C.POINTER(C.c_uint8)
@@ -96,6 +97,7 @@ SYMBOLS = [
     ("dtr_b200_get_stats", C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     ("dtr_b200_reset_stats", C.c_int, [C.c_void_p]),
     ("dtr_b200_last_pass_deferred", C.c_int, [C.c_void_p]),
+    ("dtr_b200_set_opaque_stage", C.c_int, [C.c_void_p, C.c_int]),
     ("dtr_b200_set_profiling", C.c_int, [C.c_void_p, C.c_int]),
     ("dtr_b200_get_stage_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float * 4), C.POINTER(C.c_int)]),
     ("dtr_b200_get_raster_split_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float * 2), C.POINTER(C.c_int)]),
@@ -402,8 +404,17 @@ class Renderer:
         return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
 
     def last_pass_deferred(self):
-        """True when the last flush / replay used the deferred raster stage (visibility + resolve kernels)."""
+        """True when the last flush / replay used the deferred raster stage (a pass that can never blend:
+        visibility first, every visible pixel shaded once) -- in one kernel or in two, see last_pass_stage()."""
         return bool(self.lib.dtr_b200_last_pass_deferred(self.ctx))
+
+    def last_pass_stage(self):
+        """OPAQUE_SINGLE_KERNEL (0), OPAQUE_TWO_KERNELS (1) or OPAQUE_ONE_KERNEL (2): what the last pass ran."""
+        return int(self.lib.dtr_b200_last_pass_deferred(self.ctx))
+
+    def set_opaque_stage(self, mode):
+        """How passes made only of opaque triangles onto cleared frames run from now on (dtr_b200_set_opaque_stage)."""
+        self._ck(self.lib.dtr_b200_set_opaque_stage(self.ctx, int(mode)))
 
     def reset_stats(self):
         self._ck(self.lib.dtr_b200_reset_stats(self.ctx))
@@ -421,8 +432,9 @@ class Renderer:
         return dict(setup=ms[0], scan=ms[1], bin=ms[2], raster=ms[3]), runs.value
 
     def raster_split_ms(self):
-        """Summed device ms of the raster stage's kernels: (first kernel = visibility or the single raster
-        kernel, resolve kernel), and the number of pipelines timed."""
+        """Summed device ms of the raster stage's kernels: (first kernel = the single raster kernel, the
+        one-kernel opaque stage or the visibility kernel; resolve kernel, ~0 unless the stage is two kernels),
+        and the number of pipelines timed."""
         ms, runs = (C.c_float * 2)(), C.c_int(0)
         self._ck(self.lib.dtr_b200_get_raster_split_ms(self.ctx, C.byref(ms), C.byref(runs)))
         return (ms[0], ms[1]), runs.value

@@ -99,6 +99,7 @@ struct dtr_b200_ctx
 	Geometry     geom{};
 	int          target = 0;
 	LaunchLimits limits{}; // this context's device: SM count and resident raster CTAs (queried at create)
+	int          opaqueStage = DTR_B200_OPAQUE_ONE_KERNEL; // how a pass of opaque triangles onto cleared frames runs (dtr_b200_set_opaque_stage)
 	// sort-first band exchange behind the C ABI (dtr_b200_band_comm_init / _attach)
 	NcclComm     comm = nullptr;
 	bool         ownComm = false;
@@ -153,6 +154,7 @@ struct dtr_b200_ctx
 		uint64_t listTotal = 0, triangles = 0;
 		bool     anyTextured = false; // some triangle item of the flush samples a (non-white) texture
 		bool     deferred    = false; // every primitive an opaque triangle, every frame cleared on chip: visibility + resolve
+		bool     oneKernel   = false; // ... as ONE kernel (the resolve done in place, region by region)
 		Geometry g{};
 	} last;
 
@@ -472,8 +474,8 @@ int run_pipeline(dtr_b200_ctx *c, uint32_t numActive, uint32_t numItems, uint32_
 	if (c->last.deferred)
 	{
 		// (profiling: the event between the visibility and the resolve kernel)
-		launch_raster_deferred(R, c->limits, c->stream, [](void *ctx, cudaStream_t s2) { mark(static_cast<dtr_b200_ctx *>(ctx), s2); }, c);
-		c->launches += 2;
+		launch_raster_deferred(R, c->limits, c->stream, c->last.oneKernel, [](void *ctx, cudaStream_t s2) { mark(static_cast<dtr_b200_ctx *>(ctx), s2); }, c);
+		c->launches += c->last.oneKernel ? 1 : 2;
 	}
 	else
 	{
@@ -596,14 +598,11 @@ int do_flush(dtr_b200_ctx *c)
 	// and the resolve kernel stores every pixel of the busy tiles to the output: nothing is read back over
 	// NVLink.)
 	{
-		static const bool allow = [] {
-			const char *e = getenv("DTR_B200_DEFER"); // "0": always the single-kernel raster stage
-			return !(e && e[0] == '0');
-		}();
-		bool deferred = allow && numItems > 0;
+		bool deferred = c->opaqueStage != DTR_B200_OPAQUE_SINGLE_KERNEL && numItems > 0;
 		for (uint32_t s2 = 0; s2 < numActive && deferred; s2++) deferred = (fs[s2].init & FI_COLOR_CLEAR) != 0;
 		for (uint32_t i = 0; i < numItems && deferred; i++) deferred = c->rec[i].item.type != ITEM_RAW && c->rec[i].opaque;
-		c->last.deferred = deferred;
+		c->last.deferred  = deferred;
+		c->last.oneKernel = deferred && c->opaqueStage == DTR_B200_OPAQUE_ONE_KERNEL;
 	}
 	uint32_t maxFramePrims = 0;
 	for (uint32_t s2 = 0; s2 < numActive; s2++) maxFramePrims = std::max(maxFramePrims, fs[s2].primEnd - fs[s2].primBegin);
@@ -681,6 +680,12 @@ int dtr_b200_create(int device, int width, int height, int numFrames, dtr_b200_c
 		}
 	}
 	n->limits = query_launch_limits(device);
+	// process-wide defaults from the environment (A/B runs): DTR_B200_DEFER=0 -> always the single raster kernel,
+	// DTR_B200_FUSED=0 -> opaque passes as visibility + resolve (two kernels)
+	if (const char *e = getenv("DTR_B200_FUSED"))
+		if (e[0] == '0') n->opaqueStage = DTR_B200_OPAQUE_TWO_KERNELS;
+	if (const char *e = getenv("DTR_B200_DEFER"))
+		if (e[0] == '0') n->opaqueStage = DTR_B200_OPAQUE_SINGLE_KERNEL;
 	launch_init_tables(n->ownStream);
 	n->stream = n->ownStream;
 	n->outColor = n->dColor;
@@ -1357,7 +1362,14 @@ int dtr_b200_get_stats(dtr_b200_ctx *c, dtr_b200_stats *out)
 	return DTR_B200_OK;
 }
 
-int dtr_b200_last_pass_deferred(const dtr_b200_ctx *c) { return (c && c->last.valid && c->last.deferred) ? 1 : 0; }
+int dtr_b200_last_pass_deferred(const dtr_b200_ctx *c) { return (c && c->last.valid && c->last.deferred) ? (c->last.oneKernel ? 2 : 1) : 0; }
+
+int dtr_b200_set_opaque_stage(dtr_b200_ctx *c, int mode)
+{
+	if (!c || mode < DTR_B200_OPAQUE_SINGLE_KERNEL || mode > DTR_B200_OPAQUE_ONE_KERNEL) return DTR_B200_ERR_ARG;
+	c->opaqueStage = mode;
+	return DTR_B200_OK;
+}
 
 int dtr_b200_selftest(dtr_b200_ctx *c, uint64_t *mismatches)
 {

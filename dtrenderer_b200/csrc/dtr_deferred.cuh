@@ -3,26 +3,32 @@
 // When EVERY primitive of a pass is an opaque triangle (colour alpha 1, no texture or a texture whose
 // texels all have alpha 255) and every frame of the pass starts from an on-chip clear, the colour a
 // pixel ends up with is the shading of the LAST fragment that passed the depth test there -- nothing is
-// ever blended.  The pass then runs as two kernels instead of one:
+// ever blended.  The pass then runs visibility first and shades every visible pixel ONCE (instead of once
+// per depth-test pass: 1.5 x fewer on the sphere), in one of two forms (dtr_b200_set_opaque_stage):
 //
-//   raster_vis_kernel   the same region walk as raster_kernel (list walk, depth culls, lane-parallel
-//                       setup, sub-block classification, fp32 table coverage step, strict-> depth test)
-//                       but a passing fragment only leaves its primitive's index in the colour tile
-//                       (0x80000000 | index; finished colours have a zero top byte).  No fragment
-//                       queue, no shading slots, no shading registers: 9.3 KB of shared memory per warp
-//                       and 80 registers, i.e. SIX resident CTAs per SM instead of five, and a coverage
-//                       step without the queue write.  SetPixel calls are counted here (every fragment
-//                       that passes the depth test is one, whether or not it survives).
-//   resolve_kernel      one thread per pixel of the tiles that have primitives: a pixel that still
-//                       carries an index is shaded from its triangle's record -- the int32 edge
-//                       functions are re-evaluated at the pixel (exact, so the same bits as in the
-//                       coverage step), then the reference's arithmetic (SlowTriangle :1177-1222) in
-//                       the reference's order.  Full occupancy, coalesced, every visible pixel shaded
-//                       ONCE instead of once per depth-test pass (1.5 x on the sphere).
+//   raster_opaque_kernel<true>   (default) the same region walk as raster_kernel (list walk, depth culls,
+//                       lane-parallel setup, sub-block classification, fp32 table coverage step, strict->
+//                       depth test), but a passing fragment only leaves its primitive's index in the
+//                       colour tile (0x80000000 | index; finished colours have a zero top byte).  No
+//                       fragment queue, no shading slots: 9.3 KB of shared memory per warp and 80
+//                       registers, i.e. SIX resident CTAs per SM instead of five, and a coverage step
+//                       without the queue write.  When a region's walk is over, the warp that owns it
+//                       shades the pixels that still carry an index -- from shared memory, two sub-blocks
+//                       per step as two interleaved instruction streams (the walk's registers are free by
+//                       then) -- and writes the region back once, finished.  The int32 edge functions are
+//                       re-evaluated at the pixel from the record (exact, so the same bits as in the
+//                       coverage step), then the reference's arithmetic (SlowTriangle :1177-1222) in the
+//                       reference's order.  SetPixel calls are counted in the walk (every fragment that
+//                       passes the depth test is one, whether or not it survives).
+//   raster_opaque_kernel<false> + resolve_kernel   the walk alone (the region is written back with its
+//                       pending indices), then one thread per pixel of the tiles that have primitives
+//                       shades the pixels that still carry an index: full occupancy, coalesced, but a
+//                       second pass over the busy tiles and a second kernel.  (The first form of the
+//                       stage; kept selectable: it is the measured baseline of the one-kernel form.)
 //
 // Inexact triangles (sequential fp32 accumulation, see raster_tri_replay) cannot be re-evaluated per
-// pixel without their accumulation order; their fragments are shaded at once in the visibility kernel
-// (a __noinline__ call on a path that ~2 % of mesh triangles take) and stored as finished colours.
+// pixel without their accumulation order; their fragments are shaded at once in the walk (a
+// __noinline__ call on a path that ~2 % of mesh triangles take) and stored as finished colours.
 #pragma once
 
 struct VisSmem
@@ -43,6 +49,15 @@ constexpr int      VIS_CTAS_PER_SM = 6;
 #ifndef DTR_RESOLVE_STREAMS_EMPTY
 #define DTR_RESOLVE_STREAMS_EMPTY 0
 #endif
+#ifndef DTR_FUSED_PIPE
+#define DTR_FUSED_PIPE 1 // one-kernel form: pixels of this many earlier sub-blocks are in flight (texel requested) while the next one is set up; 0 = none
+#endif
+#ifndef DTR_FUSED_CTAS
+#define DTR_FUSED_CTAS 6 // resident CTAs per SM the one-kernel form is compiled for
+#endif
+#ifndef DTR_FUSED_WIDE
+#define DTR_FUSED_WIDE 2 // one-kernel form: this many sub-blocks per step, shaded as interleaved instruction streams (0: one, with DTR_FUSED_PIPE)
+#endif
 #ifndef DTR_VIS_EMPTY_SHIFT
 #define DTR_VIS_EMPTY_SHIFT 0 // (2: no gain) log2 of the untouched tiles per work item of a large launch
 #endif
@@ -52,7 +67,71 @@ constexpr uint32_t VIS_OUTSIDE     = 0x40000000u; // resolve_kernel: a pixel of 
 // The reference's per-fragment arithmetic after the depth test for an OPAQUE fragment (SlowTriangle
 // :1177-1222, SetPixel :124-191 with a == 1): barycentrics, Gouraud, nearest texel, modulate, gamma-2
 // store.  `rec` is the triangle's 160-byte record (any address space), e1..e3 its edge functions at
-// the pixel.  Returns the packed 0x00RRGGBB pixel.
+// the pixel.  Two halves, so that a caller can have the texel of one pixel in flight while it works on
+// another: shade_opaque_lit() ends with the texel REQUEST, shade_opaque_finish() starts with its use.
+struct OpaqueLit
+{
+	float    fr, fg, fb; // lit, premultiplied linear colour before the texel
+	uint32_t texel;      // the nearest texel's word (textured triangles)
+	uint32_t ft;         // the record's flags
+};
+__device__ __forceinline__ OpaqueLit shade_opaque_lit(const uint4 *rec, const float e1, const float e2, const float e3)
+{
+	const float4   a4  = u2f4(rec[4]); // 1/area, z1, dz2, dz3
+	const float4   c   = u2f4(rec[5]); // linear premultiplied colour
+	const uint4    a6  = rec[6];       // red light products, flags | texId << 8
+	const uint32_t ft  = a6.w;
+	const float    inv = a4.x;
+	const float    bA = e1 * inv, bB = e2 * inv, bC = e3 * inv;
+	const bool     grey = (ft & PF_GREY) != 0;
+	OpaqueLit      o;
+	o.fr = c.x; o.fg = c.y; o.fb = c.z; o.texel = 0u; o.ft = ft;
+	if (!(ft & PF_IGNORE_LIGHT))
+	{
+		const float lr = ((__uint_as_float(a6.x) * bA) + (__uint_as_float(a6.y) * bB)) + (__uint_as_float(a6.z) * bC);
+		o.fr = o.fr * lr;
+		if (grey)
+		{
+			o.fg = o.fr; o.fb = o.fr; // same operands, same bits
+		}
+		else
+		{
+			const float4 a7 = u2f4(rec[7]);
+			const float4 a8 = u2f4(rec[8]);
+			const float  lg = ((a7.x * bA) + (a7.y * bB)) + (a7.z * bC);
+			const float  lb = ((a7.w * bA) + (a8.x * bB)) + (a8.y * bC);
+			o.fg = o.fg * lg; o.fb = o.fb * lb;
+		}
+	}
+	if (ft & PF_TEXTURED)
+	{
+		const uint4  t0 = rec[3]; // dy3, texels lo, texels hi, w | h << 16
+		const float4 a8 = u2f4(rec[8]), a9 = u2f4(rec[9]);
+		float u = (a8.z + (a9.x * bB)) + (a9.z * bC);
+		float v = (a8.w + (a9.y * bB)) + (a9.w * bC);
+		u = __saturatef(u); // DqnMath_Clampf(v, 0, 1): see texel_issue
+		v = __saturatef(v);
+		const uint32_t *texels = reinterpret_cast<const uint32_t *>(((unsigned long long)t0.z << 32) | t0.y);
+		const uint32_t  texW = t0.w & 0xFFFFu, texH = t0.w >> 16;
+		const uint32_t  tx = (uint32_t)(int)(u * (float)texW), ty = (uint32_t)(int)(v * (float)texH); // NEAREST
+		o.texel = __ldg(texels + (ty * texW + tx));
+	}
+	return o;
+}
+// Returns the packed 0x00RRGGBB pixel.
+__device__ __forceinline__ uint32_t shade_opaque_finish(const OpaqueLit &o)
+{
+	float      fr = o.fr, fg = o.fg, fb = o.fb;
+	const bool textured = (o.ft & PF_TEXTURED) != 0;
+	if (textured)
+	{
+		const Texel t = texel_linear(o.texel);
+		fr = fr * t.r; fg = fg * t.g; fb = fb * t.b; // (alpha: 1 * 1, the fragment is opaque by construction)
+	}
+	if ((o.ft & PF_GREY) && !textured) return out_byte(fr) * 0x010101u;
+	return (out_byte(fr) << 16) | (out_byte(fg) << 8) | out_byte(fb);
+}
+// (the one-piece form the two-kernel stage was measured with: kept as it is, the same arithmetic as the two halves)
 __device__ __forceinline__ uint32_t shade_opaque_from_record(const uint4 *rec, const float e1, const float e2, const float e3)
 {
 	const float4   a4  = u2f4(rec[4]); // 1/area, z1, dz2, dz3
@@ -105,7 +184,110 @@ __device__ __noinline__ uint32_t shade_opaque_now(const PrimRecord *rec, float e
 	return shade_opaque_from_record(reinterpret_cast<const uint4 *>(rec), e1, e2, e3);
 }
 
+// N pixels at once, for instruction-level parallelism: the same operations in the same order per pixel
+// as shade_opaque_from_record, written side by side so that the N dependency chains (and the N texel
+// fetches) overlap.  The pixels' triangles must agree in the flags that select the code path; if they
+// do not (two kinds of triangle meet in one lane's group), the pixels are shaded one after the other.
+template <int N>
+__device__ __forceinline__ void shade_opaque_wide(const uint4 *const (&rec)[N], const float (&e1)[N], const float (&e2)[N],
+                                                  const float (&e3)[N], uint32_t (&out)[N])
+{
+	float4 a4[N], c[N];
+	uint4  a6[N];
+#pragma unroll
+	for (int k = 0; k < N; k++)
+	{
+		a4[k] = ldg4f(rec[k] + 4);
+		c[k]  = ldg4f(rec[k] + 5);
+		a6[k] = __ldg(rec[k] + 6);
+	}
+	const uint32_t ft = a6[0].w;
+	uint32_t       differ = 0u;
+#pragma unroll
+	for (int k = 1; k < N; k++) differ |= ft ^ a6[k].w;
+	if (differ & (PF_GREY | PF_IGNORE_LIGHT | PF_TEXTURED))
+	{
+#pragma unroll
+		for (int k = 0; k < N; k++) out[k] = shade_opaque_now(reinterpret_cast<const PrimRecord *>(rec[k]), e1[k], e2[k], e3[k]); // (a call: rare)
+		return;
+	}
+	float bA[N], bB[N], bC[N], fr[N], fg[N], fb[N];
+#pragma unroll
+	for (int k = 0; k < N; k++)
+	{
+		const float inv = a4[k].x;
+		bA[k] = e1[k] * inv; bB[k] = e2[k] * inv; bC[k] = e3[k] * inv;
+		fr[k] = c[k].x; fg[k] = c[k].y; fb[k] = c[k].z;
+	}
+	const bool grey = (ft & PF_GREY) != 0;
+	if (!(ft & PF_IGNORE_LIGHT))
+	{
+#pragma unroll
+		for (int k = 0; k < N; k++)
+		{
+			const float lr = ((__uint_as_float(a6[k].x) * bA[k]) + (__uint_as_float(a6[k].y) * bB[k])) + (__uint_as_float(a6[k].z) * bC[k]);
+			fr[k] = fr[k] * lr;
+		}
+		if (grey)
+		{
+#pragma unroll
+			for (int k = 0; k < N; k++) { fg[k] = fr[k]; fb[k] = fr[k]; } // same operands, same bits
+		}
+		else
+		{
+#pragma unroll
+			for (int k = 0; k < N; k++)
+			{
+				const float4 a7 = ldg4f(rec[k] + 7);
+				const float4 a8 = ldg4f(rec[k] + 8);
+				const float  lg = ((a7.x * bA[k]) + (a7.y * bB[k])) + (a7.z * bC[k]);
+				const float  lb = ((a7.w * bA[k]) + (a8.x * bB[k])) + (a8.y * bC[k]);
+				fg[k] = fg[k] * lg; fb[k] = fb[k] * lb;
+			}
+		}
+	}
+	const bool textured = (ft & PF_TEXTURED) != 0;
+	if (textured)
+	{
+		uint32_t tw[N];
+#pragma unroll
+		for (int k = 0; k < N; k++)
+		{
+			const uint4  t0 = __ldg(rec[k] + 3); // dy3, texels lo, texels hi, w | h << 16
+			const float4 a8 = ldg4f(rec[k] + 8), a9 = ldg4f(rec[k] + 9);
+			float u = (a8.z + (a9.x * bB[k])) + (a9.z * bC[k]);
+			float v = (a8.w + (a9.y * bB[k])) + (a9.w * bC[k]);
+			u = __saturatef(u); // DqnMath_Clampf(v, 0, 1): see texel_issue
+			v = __saturatef(v);
+			const uint32_t *texels = reinterpret_cast<const uint32_t *>(((unsigned long long)t0.z << 32) | t0.y);
+			const uint32_t  texW = t0.w & 0xFFFFu, texH = t0.w >> 16;
+			const uint32_t  tx = (uint32_t)(int)(u * (float)texW), ty = (uint32_t)(int)(v * (float)texH); // NEAREST
+			tw[k] = __ldg(texels + (ty * texW + tx));
+		}
+#pragma unroll
+		for (int k = 0; k < N; k++)
+		{
+			const Texel t = texel_linear(tw[k]);
+			fr[k] = fr[k] * t.r; fg[k] = fg[k] * t.g; fb[k] = fb[k] * t.b; // (alpha: 1 * 1, the fragment is opaque by construction)
+		}
+	}
+	if (grey && !textured)
+	{
+#pragma unroll
+		for (int k = 0; k < N; k++) out[k] = out_byte(fr[k]) * 0x010101u;
+	}
+	else
+	{
+#pragma unroll
+		for (int k = 0; k < N; k++) out[k] = (out_byte(fr[k]) << 16) | (out_byte(fg[k]) << 8) | out_byte(fb[k]);
+	}
+}
+
+
 // One region of the visibility pass (see process_region for the walk; only the differences are commented).
+// FUSED: the pending pixels of the finished region are shaded HERE, from shared memory, before the region
+// is written back (see raster_visres_kernel); the region then leaves the SM with finished colours only.
+template <bool FUSED>
 __device__ __forceinline__ void process_region_vis(const RasterParams &P, VisSmem &W, const int lane, const RegionJob &J,
                                                    uint32_t &shaded, uint32_t &nextItem)
 {
@@ -491,6 +673,122 @@ __device__ __forceinline__ void process_region_vis(const RasterParams &P, VisSme
 	}
 	shaded += passes;
 
+	if (FUSED)
+	{
+		// ---- resolve in place: lane = pixel of a sub-block, one sub-block per step ---------------------
+		// The same arithmetic as resolve_kernel (int32 edge functions re-evaluated at the pixel from the
+		// record, then shade_opaque_from_record); the lanes of an 8x4 block mostly carry one or two tags,
+		// so the record loads of a step are a few broadcast lines.
+		// The texel of step s is requested at the end of its first half and used one step later, after the
+		// first half of step s + 1 (record fetch, edge functions, lighting): its L2 round trip runs behind
+		// that work instead of stalling the warp (DTR_FUSED_PIPE=0: one step at a time).
+		const int nSub = subsY * SUBS_X;
+#if DTR_FUSED_WIDE
+		// DTR_FUSED_WIDE horizontally adjacent sub-blocks per step (a region has SUBS_X = 4 per row), one pixel
+		// of each per lane.  A lane with pending pixels in only some of them shades one of those again in
+		// place of the others: every lane with work runs the same code.
+		constexpr int NW = DTR_FUSED_WIDE;
+		static_assert(SUBS_X % NW == 0, "a step's sub-blocks lie in one row of sub-blocks");
+		for (int s = 0; s < nSub; s += NW)
+		{
+			uint32_t v[NW];
+			bool     p[NW];
+			int      first = -1;
+#pragma unroll
+			for (int k = NW - 1; k >= 0; k--)
+			{
+				v[k] = W.c[((s + k) << 5) | lane];
+				p[k] = (v[k] & VIS_PENDING) != 0;
+				if (p[k]) first = k;
+			}
+			if (first >= 0)
+			{
+				uint32_t vf = v[0];
+#pragma unroll
+				for (int k = 1; k < NW; k++)
+					if (first == k) vf = v[k];
+				const int    y = gy + (s / SUBS_X) * SUB_H + ly; // (the step's sub-blocks lie in one row of sub-blocks)
+				const uint4 *rec[NW];
+				float        e1[NW], e2[NW], e3[NW];
+#pragma unroll
+				for (int k = 0; k < NW; k++)
+				{
+					const uint32_t t  = p[k] ? v[k] : vf;
+					const int      sk = s + (p[k] ? k : first);
+					rec[k] = reinterpret_cast<const uint4 *>(P.prims + (t & ~VIS_PENDING));
+					const uint4 q0 = __ldg(rec[k]), q1 = __ldg(rec[k] + 1), q2 = __ldg(rec[k] + 2), q3 = __ldg(rec[k] + 3);
+					const int   x  = gx + (sk & (SUBS_X - 1)) * SUB_W + lx;
+					const int   rx = x - (int)(q0.z & 0xFFFF), ry = y - (int)(q0.z >> 16);
+					e1[k] = (float)((int)q1.x + rx * (int)q1.w + ry * (int)q2.z);
+					e2[k] = (float)((int)q1.y + rx * (int)q2.x + ry * (int)q2.w);
+					e3[k] = (float)((int)q1.z + rx * (int)q2.y + ry * (int)q3.x);
+				}
+				uint32_t out[NW];
+				shade_opaque_wide<NW>(rec, e1, e2, e3, out);
+#pragma unroll
+				for (int k = 0; k < NW; k++)
+					if (p[k]) W.c[((s + k) << 5) | lane] = out[k];
+			}
+		}
+#else
+#if DTR_FUSED_PIPE
+		OpaqueLit pipe[DTR_FUSED_PIPE]; // pipe[0] = the previous step's pixel of this lane, ... (registers: every index is a constant)
+		int       pipeSi[DTR_FUSED_PIPE];
+#pragma unroll
+		for (int k = 0; k < DTR_FUSED_PIPE; k++)
+		{
+			pipe[k].fr = pipe[k].fg = pipe[k].fb = 0.0f; pipe[k].texel = 0u; pipe[k].ft = 0u;
+			pipeSi[k] = -1;
+		}
+		auto retire = [&]() { // finish the oldest pixel in flight, then everything moves up one place
+			if (pipeSi[DTR_FUSED_PIPE - 1] >= 0) W.c[pipeSi[DTR_FUSED_PIPE - 1]] = shade_opaque_finish(pipe[DTR_FUSED_PIPE - 1]);
+#pragma unroll
+			for (int k = DTR_FUSED_PIPE - 1; k > 0; k--)
+			{
+				pipe[k]   = pipe[k - 1];
+				pipeSi[k] = pipeSi[k - 1];
+			}
+			pipeSi[0] = -1;
+		};
+#endif
+		for (int s = 0; s < nSub; s++)
+		{
+			const int      si = (s << 5) | lane;
+			const uint32_t v  = W.c[si];
+#if DTR_FUSED_PIPE
+			OpaqueLit cur = pipe[0];
+			int       curSi = -1;
+#endif
+			if (v & VIS_PENDING)
+			{
+				const uint4 *rec = reinterpret_cast<const uint4 *>(P.prims + (v & ~VIS_PENDING));
+				const uint4  q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
+				const int    x = gx + (s & (SUBS_X - 1)) * SUB_W + lx, y = gy + (s / SUBS_X) * SUB_H + ly;
+				const int    rx = x - (int)(q0.z & 0xFFFF), ry = y - (int)(q0.z >> 16);
+				const int    E1 = (int)q1.x + rx * (int)q1.w + ry * (int)q2.z;
+				const int    E2 = (int)q1.y + rx * (int)q2.x + ry * (int)q2.w;
+				const int    E3 = (int)q1.z + rx * (int)q2.y + ry * (int)q3.x;
+#if DTR_FUSED_PIPE
+				cur   = shade_opaque_lit(rec, (float)E1, (float)E2, (float)E3);
+				curSi = si;
+#else
+				W.c[si] = shade_opaque_from_record(rec, (float)E1, (float)E2, (float)E3);
+#endif
+			}
+#if DTR_FUSED_PIPE
+			retire();
+			pipe[0]   = cur;
+			pipeSi[0] = curSi;
+#endif
+		}
+#if DTR_FUSED_PIPE
+#pragma unroll
+		for (int k = 0; k < DTR_FUSED_PIPE; k++) retire();
+#endif
+#endif // DTR_FUSED_WIDE
+		__syncwarp();
+	}
+
 	// ---- write the region back once (pending tags included: resolve_kernel finishes them) -----------
 	if (lane == 0) nextItem = atomicAdd(P.workCounter, 1u); // (the round trip runs behind the stores)
 	if (vec)
@@ -503,7 +801,8 @@ __device__ __forceinline__ void process_region_vis(const RasterParams &P, VisSme
 #pragma unroll 4
 		for (int i = 0; i < n; i++)
 		{
-			*pc = *reinterpret_cast<const uint4 *>(sc); // (plain stores: resolve_kernel reads these lines next)
+			if (FUSED) frame_store(pc, *reinterpret_cast<const uint4 *>(sc)); // finished colours: evict first, like the depths
+			else *pc = *reinterpret_cast<const uint4 *>(sc);                  // (plain stores: resolve_kernel reads these lines next)
 			frame_store(pz, *reinterpret_cast<const float4 *>(sz));
 			pc += width;
 			pz += width;
@@ -529,7 +828,10 @@ __device__ __forceinline__ void process_region_vis(const RasterParams &P, VisSme
 }
 
 // the persistent item loop of raster_body, for the visibility pass
-__global__ void __launch_bounds__(128, VIS_CTAS_PER_SM) raster_vis_kernel(RasterParams P)
+// (the kernels are instantiations of one __global__ template rather than wrappers around a device function: the
+// two-kernel form keeps exactly the machine code it was measured with)
+template <bool FUSED>
+__global__ void __launch_bounds__(128, FUSED ? DTR_FUSED_CTAS : VIS_CTAS_PER_SM) raster_opaque_kernel(RasterParams P)
 {
 	__shared__ __align__(16) VisSmem sW[4];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -624,7 +926,7 @@ __global__ void __launch_bounds__(128, VIS_CTAS_PER_SM) raster_vis_kernel(Raster
 		const int   tx = (int)(d1.z & 0xFFFFu), ty = (int)(d1.z >> 16);
 		const bool  genZ = (d1.y & FI_Z_RESET) != 0, genC = (d1.y & FI_COLOR_CLEAR) != 0;
 		// a tile with primitives goes to the tag planes (the context's own; resolve_kernel finishes it into the output)
-		uint32_t   *gC = (d0.y ? P.tagColor : P.color) + plane * d0.w;
+		uint32_t   *gC = ((d0.y && !FUSED) ? P.tagColor : P.color) + plane * d0.w;
 		float      *gZ = P.depth + plane * d0.w;
 		RegionJob J;
 		J.gx   = tx * TILE_W + rx;
@@ -642,13 +944,18 @@ __global__ void __launch_bounds__(128, VIS_CTAS_PER_SM) raster_vis_kernel(Raster
 		J.genZ        = genZ;
 		J.genC        = genC;
 		J.listOff     = d0.z;
-		process_region_vis(P, W, lane, J, shaded, next);
+		process_region_vis<FUSED>(P, W, lane, J, shaded, next);
 	}
 #if DTR_VIS_LANE_COUNT
 	shaded = __reduce_add_sync(0xffffffffu, shaded);
 #endif
 	if (lane == 0 && shaded) atomicAdd(P.setPixels, (unsigned long long)shaded);
 }
+
+constexpr auto raster_vis_kernel = raster_opaque_kernel<false>; // visibility only: resolve_kernel follows
+// Visibility and resolve in ONE kernel: a region's pending pixels are shaded from shared memory as soon as
+// its walk is over, by the warp that owns it; no tag planes, no second pass over the busy tiles.
+constexpr auto raster_visres_kernel = raster_opaque_kernel<true>;
 
 // Resolve: every pixel of the tiles that have primitives; a pixel that still carries a tag is shaded
 // from its triangle's record.  One CTA per busy tile (grid-stride), thread t takes pixels t + 256 k of

@@ -106,6 +106,7 @@ struct LaunchLimits
 	int sms          = 148;
 	int residentCtas = 148; // raster CTAs resident on the whole device (sms x CTAs per SM)
 	int residentCtasVis = 148; // ... of the deferred pass's visibility kernel
+	int residentCtasVisRes = 148; // ... of the one-kernel form of the deferred pass (raster_visres_kernel)
 };
 LaunchLimits query_launch_limits(int device);
 void         launch_init_tables(cudaStream_t s); // per-device lookup tables of the raster kernel (once per context)
@@ -146,9 +147,10 @@ void launch_tile_sum(const TileSumParams &P, cudaStream_t s);
 void launch_selftest_sqrt(unsigned long long *mismatches, cudaStream_t s);
 void launch_bin(const BinParams &P, const LaunchLimits &L, cudaStream_t s);
 void launch_raster(const RasterParams &P, const LaunchLimits &L, cudaStream_t s);
-// the deferred variant of the raster stage (dtr_deferred.cuh): raster_vis_kernel + resolve_kernel
-// `between` (may be null) is called after the visibility kernel has been launched: the profiling event
-void launch_raster_deferred(const RasterParams &P, const LaunchLimits &L, cudaStream_t s, void (*between)(void *, cudaStream_t) = nullptr,
+// the deferred variant of the raster stage (dtr_deferred.cuh): oneKernel = raster_opaque_kernel<true> (visibility with the
+// resolve done in place, region by region), else raster_opaque_kernel<false> (visibility) + resolve_kernel.
+// `between` (may be null) is called after the first kernel has been launched: the profiling event
+void launch_raster_deferred(const RasterParams &P, const LaunchLimits &L, cudaStream_t s, bool oneKernel, void (*between)(void *, cudaStream_t) = nullptr,
                             void *betweenArg = nullptr);
 void launch_premultiply(uint32_t *pixels, size_t count, cudaStream_t s);
 void launch_pack_bgr24(const uint32_t *color, uint32_t *out, int width, size_t rows, int pitchWords, cudaStream_t s);

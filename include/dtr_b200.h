@@ -252,9 +252,24 @@ int dtr_b200_band_barrier(dtr_b200_ctx *ctx);
  * (NCCL / peer access / torch views). */
 int dtr_b200_frame_device_ptrs(dtr_b200_ctx *ctx, int frame, void **color, void **z);
 int dtr_b200_get_stats(dtr_b200_ctx *ctx, dtr_b200_stats *out); /* syncs */
-/* 1 when the last flush / replay ran its raster stage as the deferred pair of kernels (visibility +
- * resolve: every primitive an opaque triangle, every frame cleared on chip; DTR_B200_DEFER=0 in the
- * environment turns the variant off), 0 for the single raster kernel.  Results are identical. */
+/* How the raster stage of a pass made ONLY of opaque triangles onto frames cleared on chip runs (nothing
+ * can ever be blended there: a pixel's colour is the shading of the last fragment that passed the depth
+ * test, DTRendererRender.cpp:124-191 with alpha 1).  Results are identical in every mode; every other pass
+ * takes the single raster kernel whatever the mode.
+ *   DTR_B200_OPAQUE_ONE_KERNEL (default)  visibility (depth test, primitive tags) and the shading of each
+ *                                         finished region's visible pixels in one kernel
+ *   DTR_B200_OPAQUE_TWO_KERNELS           visibility kernel, then a resolve kernel over the busy tiles
+ *   DTR_B200_OPAQUE_SINGLE_KERNEL         the general raster kernel (shades every fragment that passes)
+ * Environment (defaults of new contexts): DTR_B200_FUSED=0 -> TWO_KERNELS, DTR_B200_DEFER=0 -> SINGLE_KERNEL. */
+enum
+{
+	DTR_B200_OPAQUE_SINGLE_KERNEL = 0,
+	DTR_B200_OPAQUE_TWO_KERNELS   = 1,
+	DTR_B200_OPAQUE_ONE_KERNEL    = 2
+};
+int dtr_b200_set_opaque_stage(dtr_b200_ctx *ctx, int mode);
+/* Which of them the last flush / replay ran: 0 = the single raster kernel (the pass could blend, or the mode
+ * says so), DTR_B200_OPAQUE_TWO_KERNELS, DTR_B200_OPAQUE_ONE_KERNEL. */
 int dtr_b200_last_pass_deferred(const dtr_b200_ctx *ctx);
 int dtr_b200_reset_stats(dtr_b200_ctx *ctx);
 /* Per-stage device timing with CUDA events on the context's stream (the ncu/nsys replacement of
@@ -264,8 +279,9 @@ int dtr_b200_reset_stats(dtr_b200_ctx *ctx);
 int dtr_b200_set_profiling(dtr_b200_ctx *ctx, int enable);
 int dtr_b200_get_stage_ms(dtr_b200_ctx *ctx, float ms[4], int *runs);
 /* The raster stage of the same runs, split at the event between its kernels: ms[0] = the stage's first
- * kernel (the visibility kernel of a deferred pass, or the single raster kernel), ms[1] = the resolve
- * kernel (0 for a pass that was not deferred).  ms[0] + ms[1] = the raster entry of get_stage_ms. */
+ * kernel (the single raster kernel, the one-kernel opaque stage, or the visibility kernel of the two-kernel
+ * stage), ms[1] = the resolve kernel (~0 when the stage is one kernel).  ms[0] + ms[1] = the raster entry
+ * of get_stage_ms. */
 int dtr_b200_get_raster_split_ms(dtr_b200_ctx *ctx, float ms[2], int *runs);
 int dtr_b200_reset_stage_ms(dtr_b200_ctx *ctx);
 

@@ -36,13 +36,15 @@ def test_other_ranks_of_the_reference_arm_exit_quietly(built):
 
 
 def test_raster_stage_split_labels():
-    """roofline.raster_kernels_ms_per_step names the kernels the stage really ran: the deferred pair, or the
-    one raster kernel of a pass with blended primitives."""
+    """roofline.raster_kernels_ms_per_step names the kernels the stage really ran: the one-kernel opaque stage,
+    the visibility + resolve pair, or the one raster kernel of a pass with blended primitives."""
     sys.path.insert(0, ROOT)
     import bench
-    assert bench.kernel_split((4.0, 2.0), 2, True, True) == {"raster_vis_kernel": 2.0, "resolve_kernel": 1.0}
-    assert bench.kernel_split((4.0, 0.0), 2, False, True) == {"raster_tex_kernel": 2.0}
-    assert bench.kernel_split((4.0, 0.0), 0, False, False) == {"raster_kernel": 4.0}
+    assert bench.kernel_split((4.0, 0.0), 2, 2, True) == {"raster_opaque_kernel<true>": 2.0}
+    assert bench.kernel_split((4.0, 2.0), 2, 1, True) == {"raster_opaque_kernel<false>": 2.0, "resolve_kernel": 1.0}
+    assert bench.kernel_split((4.0, 0.0), 2, 0, True) == {"raster_tex_kernel": 2.0}
+    assert bench.kernel_split((4.0, 0.0), 0, 0, False) == {"raster_kernel": 4.0}
+    assert bench.stage_label(2, True).startswith("raster_opaque_kernel<true>") and bench.stage_label(0, False) == "raster_kernel"
 
 
 def test_gpu_arm_fails_loudly_without_a_device(built):

@@ -277,7 +277,7 @@ for f in range(2):
         r.triangle(p.reshape(-1), (*rng.random(3).tolist(), 1.0),
                    scenes.transform7(float(rng.uniform(0, 90)), (0.33, 0.33, 0.33), (1, 1, 1)) if rng.random() < 0.5 else None)
 r.flush()
-d = r.last_pass_deferred()
+d = r.last_pass_stage()
 out = hashlib.sha256()
 for f in range(2):
     col, z = r.end_frame(f)
@@ -286,11 +286,11 @@ print("RESULT", int(d), out.hexdigest(), r.stats()["setPixels"])
 """
 
 
-def _run_defer_script(env_value):
+def _run_defer_script(**overrides):
     env = dict(os.environ)
     env.pop("DTR_B200_DEFER", None)
-    if env_value is not None:
-        env["DTR_B200_DEFER"] = env_value
+    env.pop("DTR_B200_FUSED", None)
+    env.update(overrides)
     p = subprocess.run([sys.executable, "-c", _DEFER_SCRIPT % {"root": ROOT}], capture_output=True, text=True, env=env, timeout=300)
     assert p.returncode == 0, p.stderr[-2000:]
     line = [l for l in p.stdout.splitlines() if l.startswith("RESULT")][-1].split()
@@ -298,14 +298,17 @@ def _run_defer_script(env_value):
 
 
 def test_deferred_stage_equals_the_single_kernel_stage(built):
-    """A pass made of opaque triangles runs as raster_vis_kernel + resolve_kernel; DTR_B200_DEFER=0
-    forces the single-kernel stage.  Same frames (colour and depth, both frames, odd frame size,
-    exact and inexact triangles) and the same SetPixel count either way."""
-    d1, h1, n1 = _run_defer_script(None)
-    d0, h0, n0 = _run_defer_script("0")
-    assert (d1, d0) == (1, 0), "the deferred stage did not engage / did not switch off"
-    assert h1 == h0, "deferred and single-kernel frames differ"
-    assert n1 == n0, "SetPixel counts differ"
+    """A pass made of opaque triangles runs as raster_opaque_kernel<true> (visibility + in-place resolve);
+    DTR_B200_FUSED=0 makes it visibility kernel + resolve kernel, DTR_B200_DEFER=0 the single-kernel
+    stage.  Same frames (colour and depth, both frames, odd frame size, exact and inexact triangles)
+    and the same SetPixel count in all three."""
+    d2, h2, n2 = _run_defer_script()
+    d1, h1, n1 = _run_defer_script(DTR_B200_FUSED="0")
+    d0, h0, n0 = _run_defer_script(DTR_B200_DEFER="0")
+    assert (d2, d1, d0) == (2, 1, 0), "the opaque stage did not engage / did not switch"
+    assert h2 == h0, "one-kernel opaque stage and single-kernel frames differ"
+    assert h1 == h0, "two-kernel opaque stage and single-kernel frames differ"
+    assert n2 == n0 and n1 == n0, "SetPixel counts differ"
 
 
 def test_deferred_stage_only_for_passes_that_never_blend(built):
@@ -352,14 +355,17 @@ def test_fuzz_opaque_passes_take_the_deferred_stage(built, seed, size):
     flush at awkward sizes: the deferred stage engages, and colour, depth and the SetPixels counter
     equal the oracle's (the counter is order dependent: every fragment that passes the depth test when
     it is submitted counts, whether or not a later one replaces it)."""
+    from dtrenderer_b200 import api
     rng = np.random.default_rng(2000 + seed)
     w, h = size
     tex = scenes.random_texture(int(rng.integers(2, 64)), int(rng.integers(2, 64)), 30 + seed, opaque=True)
     mesh = scenes.uv_sphere(14, 7)
-    o, r = _oracle(w, h), _renderer(w, h)
+    o, r, r2 = _oracle(w, h), _renderer(w, h), _renderer(w, h)
+    r2.set_opaque_stage(api.OPAQUE_TWO_KERNELS)  # the same calls through the visibility + resolve pair
     o.reset_counters()
     r.begin_frame(0)
-    both = (o, r)
+    r2.begin_frame(0)
+    both = (o, r, r2)
     clear = tuple(rng.random(3))
     for t in both:
         t.clear(clear)
@@ -392,19 +398,22 @@ def test_fuzz_opaque_passes_take_the_deferred_stage(built, seed, size):
             pos = (float(rng.uniform(-0.3, 0.3)), 0.0, 0.0)
             for t in both:
                 t.mesh(mesh, mtex, mode, (1, -1, 1), (1, 1, 1, 1), pos, view)
-    r.flush()
-    assert r.last_pass_deferred(), "an all-opaque pass onto cleared frames did not take the deferred stage"
-    col_, z_ = r.end_frame(0)
-    _same(col_, z_, o)
-    assert r.stats()["setPixels"] == o.counters()[0]
+    for t, stage in ((r, api.OPAQUE_ONE_KERNEL), (r2, api.OPAQUE_TWO_KERNELS)):
+        t.flush()
+        assert t.last_pass_stage() == stage, "an all-opaque pass onto cleared frames did not take the deferred stage"
+        col_, z_ = t.end_frame(0)
+        _same(col_, z_, o)
+        assert t.stats()["setPixels"] == o.counters()[0]
 
 
+@pytest.mark.parametrize("stage", [2, 1])
 @pytest.mark.parametrize("two_gpus", [False, True])
-def test_deferred_stage_with_foreign_output_planes(built, two_gpus):
+def test_deferred_stage_with_foreign_output_planes(built, two_gpus, stage):
     """A band context whose output planes belong to ANOTHER context (the peer write-back of the band
-    split): the visibility kernel leaves its tags in the band context's own colour planes, the resolve
-    kernel stores every pixel of the busy tiles to the output.  Two bands of an all-opaque scene (odd
-    frame width: the scalar paths), assembled in the first context's planes, equal the oracle's frame."""
+    split).  One-kernel stage: finished regions go straight to the output.  Two-kernel stage: the
+    visibility kernel leaves its tags in the band context's own colour planes, the resolve kernel
+    stores every pixel of the busy tiles to the output.  Two bands of an all-opaque scene (odd frame
+    width: the scalar paths), assembled in the first context's planes, equal the oracle's frame."""
     import torch
     if two_gpus and torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
@@ -439,10 +448,11 @@ def test_deferred_stage_with_foreign_output_planes(built, two_gpus):
     r0.set_band(y0, y1)
     r1.set_band(*r1.band_rows(2, 1))
     for r in (r0, r1):
+        r.set_opaque_stage(stage)
         r.begin_frame(0)
         draw(r)
         r.flush()
-        assert r.last_pass_deferred()
+        assert r.last_pass_stage() == stage
     r1.sync()
     col, z = r0.end_frame(0)
     _same(col, z, o)
@@ -450,13 +460,16 @@ def test_deferred_stage_with_foreign_output_planes(built, two_gpus):
 
 
 def test_raster_stage_split_timing(built):
-    """dtr_b200_get_raster_split_ms: with profiling on, a deferred pass reports both of its kernels and
-    their sum is the raster entry of dtr_b200_get_stage_ms; a blended pass reports a single kernel."""
+    """dtr_b200_get_raster_split_ms: with profiling on, the two-kernel opaque stage reports both of its
+    kernels and their sum is the raster entry of dtr_b200_get_stage_ms; the one-kernel opaque stage and a
+    blended pass report a single kernel."""
+    from dtrenderer_b200 import api
     w, h = 640, 360
     mesh, tex = scenes.uv_sphere(), scenes.random_texture(32, 32, 4, opaque=True)
     tr = scenes.transform7(35.0, (0, 1, 0), (1, 1, 1))
-    for blended in (False, True):
+    for blended, stage in ((False, api.OPAQUE_ONE_KERNEL), (False, api.OPAQUE_TWO_KERNELS), (True, api.OPAQUE_ONE_KERNEL)):
         r = _renderer(w, h)
+        r.set_opaque_stage(stage)
         r.set_profiling(True)
         r.begin_frame(0)
         r.clear((0.3, 0.3, 0.7))
@@ -466,14 +479,14 @@ def test_raster_stage_split_timing(built):
         r.flush()
         for _ in range(3):
             r.replay()
-        stage, runs = r.stage_ms()
+        stage_ms, runs = r.stage_ms()
         (first, second), runs2 = r.raster_split_ms()
         assert runs == runs2 == 4
-        assert r.last_pass_deferred() == (not blended)
+        assert r.last_pass_stage() == (0 if blended else stage)
         assert first > 0.0
-        if blended:
+        if blended or stage == api.OPAQUE_ONE_KERNEL:
             assert second < 0.02 * runs  # an empty interval between two events: a few microseconds per run
         else:
             assert second > 0.0
-        assert abs((first + second) - stage["raster"]) <= 0.05 * stage["raster"] + 0.01
+        assert abs((first + second) - stage_ms["raster"]) <= 0.05 * stage_ms["raster"] + 0.01
         r.close()

@@ -8,8 +8,10 @@ TAG=${1:-rXX}
 MODE=${2:-bench}
 O=gpurun_out
 mkdir -p $O
-# the raster stage is raster_vis_kernel + resolve_kernel for these workloads (every primitive an opaque triangle)
-STAGE='regex:raster_vis_kernel|resolve_kernel|raster_kernel|raster_tex_kernel'
+# the raster stage is raster_opaque_kernel<true> for these workloads (every primitive an opaque triangle; with
+# DTR_B200_FUSED=0 it is raster_opaque_kernel<false> + resolve_kernel: COUNT=2 captures both)
+STAGE='regex:raster_opaque_kernel|resolve_kernel|raster_kernel|raster_tex_kernel'
+COUNT=${COUNT:-1}
 case $MODE in
 bench)
   python bench.py --steps 20 --warmup 5 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err || { tail -5 $O/${TAG}_bench.err; exit 1; }
@@ -22,12 +24,12 @@ bench)
 tex)
   CMD="python bench.py --views 64 --steps 3 --warmup 3 --no-cpu-baseline --no-others --e2e-steps 2"
   $CMD > $O/${TAG}_plain2.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k "$STAGE" -s 6 -c 2 -f -o $O/${TAG}_tex_stage $CMD > $O/${TAG}_tex_stage.log 2>&1
+  ncu --set full --clock-control none --import-source on -k "$STAGE" -s 6 -c $COUNT -f -o $O/${TAG}_tex_stage $CMD > $O/${TAG}_tex_stage.log 2>&1
   ;;
 mesh)
   CMD="python bench.py --workload mesh1080 --steps 3 --warmup 3 --no-cpu-baseline --no-others --e2e-steps 2"
   $CMD > $O/${TAG}_plain3.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k "$STAGE" -s 6 -c 2 -f -o $O/${TAG}_mesh_stage $CMD > $O/${TAG}_mesh_stage.log 2>&1
+  ncu --set full --clock-control none --import-source on -k "$STAGE" -s 6 -c $COUNT -f -o $O/${TAG}_mesh_stage $CMD > $O/${TAG}_mesh_stage.log 2>&1
   ;;
 esac
 ls -la $O | grep ${TAG}
