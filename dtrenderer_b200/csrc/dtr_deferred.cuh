@@ -49,14 +49,11 @@ constexpr int      VIS_CTAS_PER_SM = 6;
 #ifndef DTR_RESOLVE_STREAMS_EMPTY
 #define DTR_RESOLVE_STREAMS_EMPTY 0
 #endif
-#ifndef DTR_FUSED_PIPE
-#define DTR_FUSED_PIPE 1 // one-kernel form: pixels of this many earlier sub-blocks are in flight (texel requested) while the next one is set up; 0 = none
-#endif
 #ifndef DTR_FUSED_CTAS
 #define DTR_FUSED_CTAS 6 // resident CTAs per SM the one-kernel form is compiled for
 #endif
 #ifndef DTR_FUSED_WIDE
-#define DTR_FUSED_WIDE 2 // one-kernel form: this many sub-blocks per step, shaded as interleaved instruction streams (0: one, with DTR_FUSED_PIPE)
+#define DTR_FUSED_WIDE 2 // one-kernel form: this many sub-blocks per resolve step, shaded as interleaved instruction streams (1, 2 or 4)
 #endif
 #ifndef DTR_VIS_EMPTY_SHIFT
 #define DTR_VIS_EMPTY_SHIFT 0 // (2: no gain) log2 of the untouched tiles per work item of a large launch
@@ -67,71 +64,7 @@ constexpr uint32_t VIS_OUTSIDE     = 0x40000000u; // resolve_kernel: a pixel of 
 // The reference's per-fragment arithmetic after the depth test for an OPAQUE fragment (SlowTriangle
 // :1177-1222, SetPixel :124-191 with a == 1): barycentrics, Gouraud, nearest texel, modulate, gamma-2
 // store.  `rec` is the triangle's 160-byte record (any address space), e1..e3 its edge functions at
-// the pixel.  Two halves, so that a caller can have the texel of one pixel in flight while it works on
-// another: shade_opaque_lit() ends with the texel REQUEST, shade_opaque_finish() starts with its use.
-struct OpaqueLit
-{
-	float    fr, fg, fb; // lit, premultiplied linear colour before the texel
-	uint32_t texel;      // the nearest texel's word (textured triangles)
-	uint32_t ft;         // the record's flags
-};
-__device__ __forceinline__ OpaqueLit shade_opaque_lit(const uint4 *rec, const float e1, const float e2, const float e3)
-{
-	const float4   a4  = u2f4(rec[4]); // 1/area, z1, dz2, dz3
-	const float4   c   = u2f4(rec[5]); // linear premultiplied colour
-	const uint4    a6  = rec[6];       // red light products, flags | texId << 8
-	const uint32_t ft  = a6.w;
-	const float    inv = a4.x;
-	const float    bA = e1 * inv, bB = e2 * inv, bC = e3 * inv;
-	const bool     grey = (ft & PF_GREY) != 0;
-	OpaqueLit      o;
-	o.fr = c.x; o.fg = c.y; o.fb = c.z; o.texel = 0u; o.ft = ft;
-	if (!(ft & PF_IGNORE_LIGHT))
-	{
-		const float lr = ((__uint_as_float(a6.x) * bA) + (__uint_as_float(a6.y) * bB)) + (__uint_as_float(a6.z) * bC);
-		o.fr = o.fr * lr;
-		if (grey)
-		{
-			o.fg = o.fr; o.fb = o.fr; // same operands, same bits
-		}
-		else
-		{
-			const float4 a7 = u2f4(rec[7]);
-			const float4 a8 = u2f4(rec[8]);
-			const float  lg = ((a7.x * bA) + (a7.y * bB)) + (a7.z * bC);
-			const float  lb = ((a7.w * bA) + (a8.x * bB)) + (a8.y * bC);
-			o.fg = o.fg * lg; o.fb = o.fb * lb;
-		}
-	}
-	if (ft & PF_TEXTURED)
-	{
-		const uint4  t0 = rec[3]; // dy3, texels lo, texels hi, w | h << 16
-		const float4 a8 = u2f4(rec[8]), a9 = u2f4(rec[9]);
-		float u = (a8.z + (a9.x * bB)) + (a9.z * bC);
-		float v = (a8.w + (a9.y * bB)) + (a9.w * bC);
-		u = __saturatef(u); // DqnMath_Clampf(v, 0, 1): see texel_issue
-		v = __saturatef(v);
-		const uint32_t *texels = reinterpret_cast<const uint32_t *>(((unsigned long long)t0.z << 32) | t0.y);
-		const uint32_t  texW = t0.w & 0xFFFFu, texH = t0.w >> 16;
-		const uint32_t  tx = (uint32_t)(int)(u * (float)texW), ty = (uint32_t)(int)(v * (float)texH); // NEAREST
-		o.texel = __ldg(texels + (ty * texW + tx));
-	}
-	return o;
-}
-// Returns the packed 0x00RRGGBB pixel.
-__device__ __forceinline__ uint32_t shade_opaque_finish(const OpaqueLit &o)
-{
-	float      fr = o.fr, fg = o.fg, fb = o.fb;
-	const bool textured = (o.ft & PF_TEXTURED) != 0;
-	if (textured)
-	{
-		const Texel t = texel_linear(o.texel);
-		fr = fr * t.r; fg = fg * t.g; fb = fb * t.b; // (alpha: 1 * 1, the fragment is opaque by construction)
-	}
-	if ((o.ft & PF_GREY) && !textured) return out_byte(fr) * 0x010101u;
-	return (out_byte(fr) << 16) | (out_byte(fg) << 8) | out_byte(fb);
-}
-// (the one-piece form the two-kernel stage was measured with: kept as it is, the same arithmetic as the two halves)
+// the pixel.  Returns the packed 0x00RRGGBB pixel.
 __device__ __forceinline__ uint32_t shade_opaque_from_record(const uint4 *rec, const float e1, const float e2, const float e3)
 {
 	const float4   a4  = u2f4(rec[4]); // 1/area, z1, dz2, dz3
@@ -238,10 +171,10 @@ __device__ __forceinline__ void shade_opaque_wide(const uint4 *const (&rec)[N], 
 #pragma unroll
 			for (int k = 0; k < N; k++)
 			{
-				const float4 a7 = ldg4f(rec[k] + 7);
-				const float4 a8 = ldg4f(rec[k] + 8);
-				const float  lg = ((a7.x * bA[k]) + (a7.y * bB[k])) + (a7.z * bC[k]);
-				const float  lb = ((a7.w * bA[k]) + (a8.x * bB[k])) + (a8.y * bC[k]);
+				const float4 q7 = ldg4f(rec[k] + 7);
+				const float4 q8 = ldg4f(rec[k] + 8);
+				const float  lg = ((q7.x * bA[k]) + (q7.y * bB[k])) + (q7.z * bC[k]);
+				const float  lb = ((q7.w * bA[k]) + (q8.x * bB[k])) + (q8.y * bC[k]);
 				fg[k] = fg[k] * lg; fb[k] = fb[k] * lb;
 			}
 		}
@@ -253,22 +186,22 @@ __device__ __forceinline__ void shade_opaque_wide(const uint4 *const (&rec)[N], 
 #pragma unroll
 		for (int k = 0; k < N; k++)
 		{
-			const uint4  t0 = __ldg(rec[k] + 3); // dy3, texels lo, texels hi, w | h << 16
-			const float4 a8 = ldg4f(rec[k] + 8), a9 = ldg4f(rec[k] + 9);
-			float u = (a8.z + (a9.x * bB[k])) + (a9.z * bC[k]);
-			float v = (a8.w + (a9.y * bB[k])) + (a9.w * bC[k]);
+			const uint4  t  = __ldg(rec[k] + 3); // dy3, texels lo, texels hi, w | h << 16
+			const float4 q8 = ldg4f(rec[k] + 8), q9 = ldg4f(rec[k] + 9);
+			float u = (q8.z + (q9.x * bB[k])) + (q9.z * bC[k]);
+			float v = (q8.w + (q9.y * bB[k])) + (q9.w * bC[k]);
 			u = __saturatef(u); // DqnMath_Clampf(v, 0, 1): see texel_issue
 			v = __saturatef(v);
-			const uint32_t *texels = reinterpret_cast<const uint32_t *>(((unsigned long long)t0.z << 32) | t0.y);
-			const uint32_t  texW = t0.w & 0xFFFFu, texH = t0.w >> 16;
+			const uint32_t *texels = reinterpret_cast<const uint32_t *>(((unsigned long long)t.z << 32) | t.y);
+			const uint32_t  texW = t.w & 0xFFFFu, texH = t.w >> 16;
 			const uint32_t  tx = (uint32_t)(int)(u * (float)texW), ty = (uint32_t)(int)(v * (float)texH); // NEAREST
 			tw[k] = __ldg(texels + (ty * texW + tx));
 		}
 #pragma unroll
 		for (int k = 0; k < N; k++)
 		{
-			const Texel t = texel_linear(tw[k]);
-			fr[k] = fr[k] * t.r; fg[k] = fg[k] * t.g; fb[k] = fb[k] * t.b; // (alpha: 1 * 1, the fragment is opaque by construction)
+			const Texel tl = texel_linear(tw[k]);
+			fr[k] = fr[k] * tl.r; fg[k] = fg[k] * tl.g; fb[k] = fb[k] * tl.b; // (alpha: 1 * 1, the fragment is opaque by construction)
 		}
 	}
 	if (grey && !textured)
@@ -675,15 +608,11 @@ __device__ __forceinline__ void process_region_vis(const RasterParams &P, VisSme
 
 	if (FUSED)
 	{
-		// ---- resolve in place: lane = pixel of a sub-block, one sub-block per step ---------------------
+		// ---- resolve in place ------------------------------------------------------------------------
 		// The same arithmetic as resolve_kernel (int32 edge functions re-evaluated at the pixel from the
-		// record, then shade_opaque_from_record); the lanes of an 8x4 block mostly carry one or two tags,
-		// so the record loads of a step are a few broadcast lines.
-		// The texel of step s is requested at the end of its first half and used one step later, after the
-		// first half of step s + 1 (record fetch, edge functions, lighting): its L2 round trip runs behind
-		// that work instead of stalling the warp (DTR_FUSED_PIPE=0: one step at a time).
+		// record, then the reference's shading); lane = pixel of a sub-block.  The lanes of an 8x4 block
+		// mostly carry one or two tags, so the record loads of a step are a few broadcast lines.
 		const int nSub = subsY * SUBS_X;
-#if DTR_FUSED_WIDE
 		// DTR_FUSED_WIDE horizontally adjacent sub-blocks per step (a region has SUBS_X = 4 per row), one pixel
 		// of each per lane.  A lane with pending pixels in only some of them shades one of those again in
 		// place of the others: every lane with work runs the same code.
@@ -730,62 +659,6 @@ __device__ __forceinline__ void process_region_vis(const RasterParams &P, VisSme
 					if (p[k]) W.c[((s + k) << 5) | lane] = out[k];
 			}
 		}
-#else
-#if DTR_FUSED_PIPE
-		OpaqueLit pipe[DTR_FUSED_PIPE]; // pipe[0] = the previous step's pixel of this lane, ... (registers: every index is a constant)
-		int       pipeSi[DTR_FUSED_PIPE];
-#pragma unroll
-		for (int k = 0; k < DTR_FUSED_PIPE; k++)
-		{
-			pipe[k].fr = pipe[k].fg = pipe[k].fb = 0.0f; pipe[k].texel = 0u; pipe[k].ft = 0u;
-			pipeSi[k] = -1;
-		}
-		auto retire = [&]() { // finish the oldest pixel in flight, then everything moves up one place
-			if (pipeSi[DTR_FUSED_PIPE - 1] >= 0) W.c[pipeSi[DTR_FUSED_PIPE - 1]] = shade_opaque_finish(pipe[DTR_FUSED_PIPE - 1]);
-#pragma unroll
-			for (int k = DTR_FUSED_PIPE - 1; k > 0; k--)
-			{
-				pipe[k]   = pipe[k - 1];
-				pipeSi[k] = pipeSi[k - 1];
-			}
-			pipeSi[0] = -1;
-		};
-#endif
-		for (int s = 0; s < nSub; s++)
-		{
-			const int      si = (s << 5) | lane;
-			const uint32_t v  = W.c[si];
-#if DTR_FUSED_PIPE
-			OpaqueLit cur = pipe[0];
-			int       curSi = -1;
-#endif
-			if (v & VIS_PENDING)
-			{
-				const uint4 *rec = reinterpret_cast<const uint4 *>(P.prims + (v & ~VIS_PENDING));
-				const uint4  q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
-				const int    x = gx + (s & (SUBS_X - 1)) * SUB_W + lx, y = gy + (s / SUBS_X) * SUB_H + ly;
-				const int    rx = x - (int)(q0.z & 0xFFFF), ry = y - (int)(q0.z >> 16);
-				const int    E1 = (int)q1.x + rx * (int)q1.w + ry * (int)q2.z;
-				const int    E2 = (int)q1.y + rx * (int)q2.x + ry * (int)q2.w;
-				const int    E3 = (int)q1.z + rx * (int)q2.y + ry * (int)q3.x;
-#if DTR_FUSED_PIPE
-				cur   = shade_opaque_lit(rec, (float)E1, (float)E2, (float)E3);
-				curSi = si;
-#else
-				W.c[si] = shade_opaque_from_record(rec, (float)E1, (float)E2, (float)E3);
-#endif
-			}
-#if DTR_FUSED_PIPE
-			retire();
-			pipe[0]   = cur;
-			pipeSi[0] = curSi;
-#endif
-		}
-#if DTR_FUSED_PIPE
-#pragma unroll
-		for (int k = 0; k < DTR_FUSED_PIPE; k++) retire();
-#endif
-#endif // DTR_FUSED_WIDE
 		__syncwarp();
 	}
 

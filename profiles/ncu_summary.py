@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Turn one `ncu --set full` report into the summaries kept under profiles/.  A report may hold several
-kernels (the deferred raster stage is raster_vis_kernel + resolve_kernel, captured in one ncu pass);
+kernels (the two-kernel opaque stage is raster_opaque_kernel<0> + resolve_kernel, captured in one ncu pass);
 per kernel <k>:
    <tag>_<k>_details.txt  (ncu --page details), <tag>_<k>_raw.json (selected raw metrics),
    <tag>_<k>_lines.txt (per-source-line shares, ncu_lines.py)
@@ -47,17 +47,18 @@ kernels = []
 for vals in rows[2:]:
     if len(vals) <= ik:
         continue
-    short = vals[ik].split("(")[0].split("::")[-1]
-    if short in [k for k, _ in kernels]:
+    full = vals[ik].split("(")[0].split("::")[-1].replace("void ", "").strip()  # e.g. raster_opaque_kernel<1>
+    short = full.replace("<", "_").replace(">", "")                              # file names: raster_opaque_kernel_1
+    if short in [k for k, _, _ in kernels]:
         continue  # (one launch per kernel is summarised: the first)
-    kernels.append((short, {n: {"value": v, "unit": u} for n, u, v in zip(names, units, vals) if n in WANT}))
+    kernels.append((short, full.split("<")[0], {n: {"value": v, "unit": u} for n, u, v in zip(names, units, vals) if n in WANT}))
 
 read = write = 0.0
 parts = []
-for short, out in kernels:
+for short, base, out in kernels:
     json.dump(out, open(os.path.join(here, f"{tag}_{short}_raw.json"), "w"), indent=1)
-    open(os.path.join(here, f"{tag}_{short}_details.txt"), "w").write(ncu("--page", "details", "--kernel-name", short))
-    src = ncu("--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", short)
+    open(os.path.join(here, f"{tag}_{short}_details.txt"), "w").write(ncu("--page", "details", "--kernel-name", base))
+    src = ncu("--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", base)
     tmp = f"/tmp/{tag}_{short}_both.csv"
     open(tmp, "w").write(src)
     lines = subprocess.run([sys.executable, os.path.join(here, "ncu_lines.py"), tmp, "60"], capture_output=True, text=True).stdout
