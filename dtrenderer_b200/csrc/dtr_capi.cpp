@@ -594,9 +594,10 @@ int do_flush(dtr_b200_ctx *c)
 	for (uint32_t i = 0; i < numItems; i++) c->last.anyTextured = c->last.anyTextured || (it[i].type != ITEM_RAW && it[i].texId >= 0);
 	// Deferred pass (dtr_deferred.cuh): only when nothing can ever be blended -- every primitive an opaque
 	// triangle, every frame starting from an on-chip clear.  (With foreign output planes -- a band written
-	// into another GPU's frame -- the visibility kernel leaves its tags in this context's own colour planes
-	// and the resolve kernel stores every pixel of the busy tiles to the output: nothing is read back over
-	// NVLink.)
+	// into another GPU's frame -- the one-kernel form stores finished regions straight to the output; in
+	// the two-kernel form the visibility kernel leaves its tags in this context's own colour planes and
+	// the resolve kernel stores every pixel of the busy tiles to the output.  Nothing is ever read back
+	// over NVLink.)
 	{
 		bool deferred = c->opaqueStage != DTR_B200_OPAQUE_SINGLE_KERNEL && numItems > 0;
 		for (uint32_t s2 = 0; s2 < numActive && deferred; s2++) deferred = (fs[s2].init & FI_COLOR_CLEAR) != 0;

@@ -74,7 +74,7 @@ struct RasterParams
 {
 	uint32_t           *color; // [F][H][W]
 	float              *depth;
-	uint32_t           *tagColor; // deferred stage: where the visibility kernel leaves the colour tiles of busy tiles (pending
+	uint32_t           *tagColor; // two-kernel deferred stage: where the visibility kernel leaves the colour tiles of busy tiles (pending
 	                              // tags included) for the resolve kernel -- the context's OWN colour planes; == color unless
 	                              // the output planes are foreign (another GPU's memory)
 	const FrameState   *frames;
