@@ -18,5 +18,5 @@ except Exception as e:
     print('FAILED', e, open('gpurun_out/${TAG}_$1.err').read()[-1500:])
 P
 }
-for f in ${ORDER:-1 0}; do run base_f$f $f /root/repo/dtrenderer_b200/libdtr_b200.so; done
+if [ "${BASE:-1}" != "0" ]; then for f in ${ORDER:-1 0}; do run base_f$f $f /root/repo/dtrenderer_b200/libdtr_b200.so; done; fi
 for v in "$@"; do run $v 1 /root/repo/variants/libdtr_$v.so; done
