@@ -92,6 +92,21 @@ def test_band_exchange_entry_points_fail_loudly_without_a_context(built):
     assert lib.dtr_b200_band_comm_init(None, None, 2, 0) == -1
 
 
+def test_opaque_stage_selector_rejects_bad_arguments(built):
+    """dtr_b200_set_opaque_stage: no context -> ERR_ARG; the header's three modes are what the binding names;
+    without a context nothing ran, so dtr_b200_last_pass_deferred is 0."""
+    import re
+    from dtrenderer_b200 import api
+    lib = api.load_library()
+    for mode in (0, 1, 2, 3, -1):
+        assert lib.dtr_b200_set_opaque_stage(None, mode) == -1
+    assert lib.dtr_b200_last_pass_deferred(None) == 0
+    hdr = open(os.path.join(ROOT, "include", "dtr_b200.h")).read()
+    enum = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"DTR_B200_(OPAQUE_\w+)\s*=\s*(\d+)", hdr))
+    assert enum == {"OPAQUE_SINGLE_KERNEL": api.OPAQUE_SINGLE_KERNEL, "OPAQUE_TWO_KERNELS": api.OPAQUE_TWO_KERNELS,
+                    "OPAQUE_ONE_KERNEL": api.OPAQUE_ONE_KERNEL}
+
+
 def test_library_has_no_link_time_nccl_dependency(built):
     """NCCL is bound with dlopen at the first band call; a host without NCCL can still load the module."""
     from dtrenderer_b200 import api
