@@ -1,4 +1,4 @@
-# A/B of the one-kernel form of the opaque-only raster stage (DTR_B200_FUSED=1: raster_vis_kernel_t<true>) against
+# A/B of the one-kernel form of the opaque-only raster stage (the default: raster_opaque_kernel<true>; DTR_B200_FUSED=0 selects the pair) against
 # visibility + resolve, same box: bench.py's default line (512 textured 1080p views) with its other_workloads,
 # every number parity checked by bench.py itself.
 # usage: gpurun -- bash tools/ab_fused.sh <tag> [variant...]     (variants/libdtr_<variant>.so, run with DTR_B200_FUSED=1)
